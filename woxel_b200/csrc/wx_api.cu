@@ -1,0 +1,659 @@
+// wx_api.cu -- the C ABI of include/woxel_b200.h: context, tree packing/upload, frame entry points.
+//
+// Replaces the wgpu plumbing of the reference around its compute pass: device creation
+// (src/render/wgpu_context.rs:33-99), model upload (:101-159, :506-573) and the per-frame encode
+// + dispatch (:207-292).  Unlike the reference, nothing is re-created per frame (:219-268 builds
+// pipelines, layouts and textures on every redraw): buffers, streams and events live in the context.
+#include <algorithm>
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "wx_device.cuh"
+#include "wx_internal.h"
+
+using namespace wx;
+
+// ---------------------------------------------------------------------------------------------
+// Context
+// ---------------------------------------------------------------------------------------------
+struct DeviceSlot {
+  int id = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool events_pending = false;
+  bool peer_to_first = false;  // can store straight into device[0] memory
+  WxState* d_states = nullptr;
+  uint32_t states_cap = 0;
+  uint8_t* scratch = nullptr;  // staging frame when peer stores are impossible
+  size_t scratch_bytes = 0;
+};
+
+struct FrameBuffers {  // device[0]-resident outputs of wx_render
+  uint8_t* rgba = nullptr;
+  size_t rgba_bytes = 0;
+  void* aov[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  size_t aov_bytes[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+};
+
+struct WxContext {
+  std::vector<DeviceSlot> dev;
+  FrameBuffers fb;
+  cudaEvent_t total0 = nullptr, total1 = nullptr;
+  bool total_pending = false;
+  WxRenderInfo info{};
+  std::string last_error;
+};
+
+struct TreeOnDevice {
+  uint32_t *e5 = nullptr, *e4 = nullptr, *l3 = nullptr;
+  int4* origins = nullptr;
+};
+
+struct WxTree {
+  WxContext* ctx = nullptr;
+  std::vector<TreeOnDevice> on;  // one per context device
+  std::vector<int4> origins;
+  WxTreeInfo info{};
+};
+
+static thread_local std::string g_last_error;  // failures before a context exists
+
+static int fail(WxContext* ctx, int status, const std::string& what) {
+  if (ctx) ctx->last_error = what;
+  g_last_error = what;
+  return status;
+}
+static int fail_cuda(WxContext* ctx, cudaError_t e, const char* where) {
+  std::string msg = std::string(where) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")";
+  (void)cudaGetLastError();  // clear the sticky-free error state
+  return fail(ctx, e == cudaErrorMemoryAllocation ? WX_ERR_OUT_OF_MEMORY : WX_ERR_CUDA, msg);
+}
+#define WX_CUDA(ctx, call)                                      \
+  do {                                                          \
+    cudaError_t e_ = (call);                                    \
+    if (e_ != cudaSuccess) return fail_cuda((ctx), e_, #call);  \
+  } while (0)
+
+extern "C" int wx_abi_version(void) { return WX_ABI_VERSION; }
+
+extern "C" const char* wx_strerror(int status) {
+  switch (status) {
+    case WX_OK: return "ok";
+    case WX_ERR_INVALID_ARGUMENT: return "invalid argument";
+    case WX_ERR_NO_DEVICE: return "no CUDA device available (this path has no CPU fallback)";
+    case WX_ERR_CUDA: return "CUDA runtime error";
+    case WX_ERR_OUT_OF_MEMORY: return "out of device memory";
+    case WX_ERR_BAD_TREE: return "inconsistent tree description";
+    case WX_ERR_UNSUPPORTED: return "unsupported input";
+    case WX_ERR_PEER_ACCESS: return "peer access unavailable";
+    default: return "unknown status";
+  }
+}
+
+extern "C" const char* wx_last_error(const WxContext* ctx) { return ctx ? ctx->last_error.c_str() : g_last_error.c_str(); }
+
+extern "C" int wx_init(int n_devices, const int* device_ids, WxContext** out) {
+  if (!out || n_devices < 0) return fail(nullptr, WX_ERR_INVALID_ARGUMENT, "wx_init: bad arguments");
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    (void)cudaGetLastError();
+    return fail(nullptr, WX_ERR_NO_DEVICE, std::string("wx_init: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "0 devices"));
+  }
+  WxContext* ctx = new (std::nothrow) WxContext();
+  if (!ctx) return WX_ERR_OUT_OF_MEMORY;
+  int current = 0;
+  (void)cudaGetDevice(&current);
+  const int n = n_devices == 0 ? 1 : n_devices;
+  for (int i = 0; i < n; ++i) {
+    DeviceSlot s;
+    s.id = n_devices == 0 ? current : (device_ids ? device_ids[i] : i);
+    if (s.id < 0 || s.id >= count) {
+      delete ctx;
+      return fail(nullptr, WX_ERR_INVALID_ARGUMENT, "wx_init: device id out of range");
+    }
+    ctx->dev.push_back(s);
+  }
+  for (size_t i = 0; i < ctx->dev.size(); ++i) {
+    DeviceSlot& s = ctx->dev[i];
+    cudaError_t err = cudaSetDevice(s.id);
+    if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking);
+    if (err == cudaSuccess) err = cudaEventCreate(&s.ev0);
+    if (err == cudaSuccess) err = cudaEventCreate(&s.ev1);
+    if (err != cudaSuccess) {
+      int rc = fail_cuda(nullptr, err, "wx_init: stream/event creation");
+      wx_shutdown(ctx);
+      return rc;
+    }
+    if (i > 0) {
+      int can = 0;
+      if (cudaDeviceCanAccessPeer(&can, s.id, ctx->dev[0].id) == cudaSuccess && can) {
+        cudaError_t pe = cudaDeviceEnablePeerAccess(ctx->dev[0].id, 0);
+        s.peer_to_first = (pe == cudaSuccess || pe == cudaErrorPeerAccessAlreadyEnabled);
+      }
+      (void)cudaGetLastError();
+    }
+  }
+  (void)cudaSetDevice(ctx->dev[0].id);
+  if (cudaEventCreate(&ctx->total0) != cudaSuccess || cudaEventCreate(&ctx->total1) != cudaSuccess) {
+    int rc = fail_cuda(nullptr, cudaGetLastError(), "wx_init: event creation");
+    wx_shutdown(ctx);
+    return rc;
+  }
+  *out = ctx;
+  return WX_OK;
+}
+
+static void free_frame_buffers(WxContext* ctx) {
+  if (ctx->dev.empty()) return;
+  (void)cudaSetDevice(ctx->dev[0].id);
+  if (ctx->fb.rgba) (void)cudaFree(ctx->fb.rgba);
+  for (auto& p : ctx->fb.aov)
+    if (p) (void)cudaFree(p);
+  ctx->fb = FrameBuffers();
+}
+
+extern "C" int wx_shutdown(WxContext* ctx) {
+  if (!ctx) return WX_OK;
+  free_frame_buffers(ctx);
+  for (DeviceSlot& s : ctx->dev) {
+    (void)cudaSetDevice(s.id);
+    if (s.stream) (void)cudaStreamSynchronize(s.stream);
+    if (s.d_states) (void)cudaFree(s.d_states);
+    if (s.scratch) (void)cudaFree(s.scratch);
+    if (s.ev0) (void)cudaEventDestroy(s.ev0);
+    if (s.ev1) (void)cudaEventDestroy(s.ev1);
+    if (s.stream) (void)cudaStreamDestroy(s.stream);
+  }
+  if (ctx->total0) (void)cudaEventDestroy(ctx->total0);
+  if (ctx->total1) (void)cudaEventDestroy(ctx->total1);
+  delete ctx;
+  return WX_OK;
+}
+
+extern "C" int wx_device_count(const WxContext* ctx) { return ctx ? (int)ctx->dev.size() : 0; }
+
+// ---------------------------------------------------------------------------------------------
+// Tree packing: WxTreeDesc (reference order: masks + per-slot u32) -> entry tables + leaf bricks
+// ---------------------------------------------------------------------------------------------
+template <class F>
+static void parallel_for(size_t n, F&& f) {
+  unsigned hw = std::thread::hardware_concurrency();
+  size_t nt = std::min<size_t>(hw ? hw : 1, std::max<size_t>(1, n / 64));
+  if (nt <= 1) {
+    for (size_t i = 0; i < n; ++i) f(i);
+    return;
+  }
+  std::atomic<size_t> next{0};
+  std::vector<std::thread> th;
+  auto body = [&]() {
+    for (;;) {
+      size_t b = next.fetch_add(256);
+      if (b >= n) break;
+      size_t e = std::min(n, b + 256);
+      for (size_t i = b; i < e; ++i) f(i);
+    }
+  };
+  for (size_t t = 1; t < nt; ++t) th.emplace_back(body);
+  body();
+  for (auto& t : th) t.join();
+}
+
+static inline bool bit(const uint64_t* m, size_t i) { return (m[i >> 6] >> (i & 63)) & 1ull; }
+
+// One internal level.  Returns 0, or a negative status; *max_dist receives the largest tile distance.
+static int pack_internal(uint32_t n_nodes, uint32_t slots, const uint64_t* kids, const uint64_t* vals, const uint32_t* tab,
+                         uint32_t n_children, std::vector<uint32_t>& out, uint32_t* max_dist) {
+  out.assign((size_t)n_nodes * slots, 0u);
+  std::atomic<int> status{0};
+  std::atomic<uint32_t> mx{0};
+  parallel_for(n_nodes, [&](size_t node) {
+    const uint64_t* k = kids + node * (slots / 64);
+    const uint64_t* v = vals + node * (slots / 64);
+    const uint32_t* t = tab + node * slots;
+    uint32_t* o = out.data() + node * slots;
+    uint32_t local_max = 0;
+    for (uint32_t s = 0; s < slots; ++s) {
+      if (bit(v, s)) {
+        o[s] = 0u;  // active tile: a hit, whatever the child bit says (raycast.comp.wgsl:431-433)
+      } else if (bit(k, s)) {
+        if (t[s] >= n_children) {
+          status.store(WX_ERR_BAD_TREE);
+          return;
+        }
+        o[s] = kChildFlag | t[s];
+      } else {
+        if (t[s] & kChildFlag) {
+          status.store(WX_ERR_UNSUPPORTED);
+          return;
+        }
+        o[s] = t[s];
+        local_max = std::max(local_max, t[s]);
+      }
+    }
+    uint32_t cur = mx.load();
+    while (local_max > cur && !mx.compare_exchange_weak(cur, local_max)) {
+    }
+  });
+  *max_dist = mx.load();
+  return status.load();
+}
+
+extern "C" int wx_tree_upload(WxContext* ctx, const WxTreeDesc* d, WxTree** out) {
+  if (!ctx || !d || !out) return fail(ctx, WX_ERR_INVALID_ARGUMENT, "wx_tree_upload: null argument");
+  *out = nullptr;
+  if ((d->n5 && (!d->origins || !d->kids5 || !d->vals5 || !d->tab5)) || (d->n4 && (!d->kids4 || !d->vals4 || !d->tab4)) ||
+      (d->n3 && (!d->vals3 || !d->tab3)))
+    return fail(ctx, WX_ERR_INVALID_ARGUMENT, "wx_tree_upload: missing array");
+  if (d->n3 && d->tab3_elem_bytes != 1 && d->tab3_elem_bytes != 4)
+    return fail(ctx, WX_ERR_INVALID_ARGUMENT, "wx_tree_upload: tab3_elem_bytes must be 1 or 4");
+  if (d->n4 >= kChildFlag || d->n3 >= kChildFlag) return fail(ctx, WX_ERR_UNSUPPORTED, "wx_tree_upload: too many nodes");
+
+  std::vector<uint32_t> e5, e4, l3;
+  uint32_t max5 = 0, max4 = 0;
+  int rc = pack_internal(d->n5, 32768, d->kids5, d->vals5, d->tab5, d->n4, e5, &max5);
+  if (rc) return fail(ctx, rc, "wx_tree_upload: N5 table (child index out of range or distance >= 2^31)");
+  rc = pack_internal(d->n4, 4096, d->kids4, d->vals4, d->tab4, d->n3, e4, &max4);
+  if (rc) return fail(ctx, rc, "wx_tree_upload: N4 table (child index out of range or distance >= 2^31)");
+
+  // leaf distance width: the largest inactive-voxel distance decides
+  const uint8_t* t8 = (const uint8_t*)d->tab3;
+  const uint32_t* t32 = (const uint32_t*)d->tab3;
+  const bool narrow = d->tab3_elem_bytes == 1;
+  std::atomic<uint32_t> mx3{0};
+  parallel_for(d->n3, [&](size_t leaf) {
+    const uint64_t* v = d->vals3 + leaf * 8;
+    uint32_t local_max = 0;
+    for (uint32_t s = 0; s < 512; ++s)
+      if (!bit(v, s)) local_max = std::max(local_max, narrow ? (uint32_t)t8[leaf * 512 + s] : t32[leaf * 512 + s]);
+    uint32_t cur = mx3.load();
+    while (local_max > cur && !mx3.compare_exchange_weak(cur, local_max)) {
+    }
+  });
+  const uint32_t max3v = mx3.load();
+  const uint32_t leaf_bits = max3v <= 15 ? 4 : (max3v <= 255 ? 8 : 32);
+  const size_t words_per_leaf = leaf_bits == 4 ? 64 : (leaf_bits == 8 ? 128 : 512);
+  l3.assign((size_t)d->n3 * words_per_leaf, 0u);
+  parallel_for(d->n3, [&](size_t leaf) {
+    const uint64_t* v = d->vals3 + leaf * 8;
+    uint32_t* o = l3.data() + leaf * words_per_leaf;
+    for (uint32_t s = 0; s < 512; ++s) {
+      const uint32_t dist = bit(v, s) ? 0u : (narrow ? (uint32_t)t8[leaf * 512 + s] : t32[leaf * 512 + s]);
+      if (leaf_bits == 4) o[s >> 3] |= dist << ((s & 7) * 4);
+      else if (leaf_bits == 8) o[s >> 2] |= dist << ((s & 3) * 8);
+      else o[s] = dist;
+    }
+  });
+
+  WxTree* t = new (std::nothrow) WxTree();
+  if (!t) return fail(ctx, WX_ERR_OUT_OF_MEMORY, "wx_tree_upload: host allocation");
+  t->ctx = ctx;
+  t->origins.resize(d->n5);
+  for (uint32_t i = 0; i < d->n5; ++i) t->origins[i] = make_int4(d->origins[3 * i], d->origins[3 * i + 1], d->origins[3 * i + 2], 0);
+  t->info.n5 = d->n5, t->info.n4 = d->n4, t->info.n3 = d->n3;
+  t->info.leaf_bits = leaf_bits;
+  t->info.max_dist[0] = max5, t->info.max_dist[1] = max4, t->info.max_dist[2] = max3v;
+  t->info.n_devices = (uint32_t)ctx->dev.size();
+  t->info.device_bytes = (e5.size() + e4.size() + l3.size()) * 4 + t->origins.size() * sizeof(int4);
+  t->on.resize(ctx->dev.size());
+
+  auto up = [&](int dev_i) -> int {
+    DeviceSlot& s = ctx->dev[dev_i];
+    TreeOnDevice& o = t->on[dev_i];
+    WX_CUDA(ctx, cudaSetDevice(s.id));
+    // +256 B of slack keeps zero-sized levels allocatable
+    WX_CUDA(ctx, cudaMalloc(&o.e5, e5.size() * 4 + 256));
+    WX_CUDA(ctx, cudaMalloc(&o.e4, e4.size() * 4 + 256));
+    WX_CUDA(ctx, cudaMalloc(&o.l3, l3.size() * 4 + 256));
+    WX_CUDA(ctx, cudaMalloc(&o.origins, t->origins.size() * sizeof(int4) + 256));
+    if (!e5.empty()) WX_CUDA(ctx, cudaMemcpyAsync(o.e5, e5.data(), e5.size() * 4, cudaMemcpyHostToDevice, s.stream));
+    if (!e4.empty()) WX_CUDA(ctx, cudaMemcpyAsync(o.e4, e4.data(), e4.size() * 4, cudaMemcpyHostToDevice, s.stream));
+    if (!l3.empty()) WX_CUDA(ctx, cudaMemcpyAsync(o.l3, l3.data(), l3.size() * 4, cudaMemcpyHostToDevice, s.stream));
+    if (!t->origins.empty())
+      WX_CUDA(ctx, cudaMemcpyAsync(o.origins, t->origins.data(), t->origins.size() * sizeof(int4), cudaMemcpyHostToDevice, s.stream));
+    return WX_OK;
+  };
+  for (int i = 0; i < (int)ctx->dev.size(); ++i) {
+    rc = up(i);
+    if (rc) {
+      wx_tree_free(ctx, t);
+      return rc;
+    }
+  }
+  for (DeviceSlot& s : ctx->dev) {
+    (void)cudaSetDevice(s.id);
+    cudaError_t e = cudaStreamSynchronize(s.stream);
+    if (e != cudaSuccess) {
+      wx_tree_free(ctx, t);
+      return fail_cuda(ctx, e, "wx_tree_upload: synchronize");
+    }
+  }
+  (void)cudaSetDevice(ctx->dev[0].id);
+  *out = t;
+  return WX_OK;
+}
+
+extern "C" int wx_tree_free(WxContext* ctx, WxTree* tree) {
+  if (!tree) return WX_OK;
+  WxContext* c = ctx ? ctx : tree->ctx;
+  for (size_t i = 0; i < tree->on.size() && c && i < c->dev.size(); ++i) {
+    (void)cudaSetDevice(c->dev[i].id);
+    TreeOnDevice& o = tree->on[i];
+    if (o.e5) (void)cudaFree(o.e5);
+    if (o.e4) (void)cudaFree(o.e4);
+    if (o.l3) (void)cudaFree(o.l3);
+    if (o.origins) (void)cudaFree(o.origins);
+  }
+  delete tree;
+  return WX_OK;
+}
+
+extern "C" int wx_tree_info(const WxTree* tree, WxTreeInfo* info) {
+  if (!tree || !info) return WX_ERR_INVALID_ARGUMENT;
+  *info = tree->info;
+  return WX_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Frame entry points
+// ---------------------------------------------------------------------------------------------
+static int launch_on(WxContext* ctx, int dev_i, const WxTree* tree, const WxState* states, uint32_t n_states, uint32_t width,
+                     uint32_t height, uint8_t* rgba_dev, const WxAov* aov_dev, const WxShard* shard, cudaStream_t stream,
+                     uint32_t* launches_out) {
+  DeviceSlot& s = ctx->dev[dev_i];
+  const TreeOnDevice& o = tree->on[dev_i];
+  RenderParams P;
+  memset(&P, 0, sizeof(P));
+  P.tree.e5 = o.e5, P.tree.e4 = o.e4, P.tree.l3 = o.l3, P.tree.origins_g = o.origins;
+  P.tree.n5 = tree->info.n5, P.tree.n4 = tree->info.n4, P.tree.n3 = tree->info.n3;
+  P.tree.leaf_bits = tree->info.leaf_bits;
+  for (uint32_t i = 0; i < kInlineOrigins && i < tree->info.n5; ++i) P.tree.origins_c[i] = tree->origins[i];
+  P.n_states = n_states;
+  P.width = width, P.height = height;
+  P.rgba = reinterpret_cast<uchar4*>(rgba_dev);
+  if (aov_dev) {
+    P.aov.state = aov_dev->state, P.aov.voxel = aov_dev->voxel, P.aov.leaf = aov_dev->leaf, P.aov.level = aov_dev->level;
+    P.aov.iters = aov_dev->iters, P.aov.depth = aov_dev->depth, P.aov.mask = aov_dev->mask, P.aov.pos = aov_dev->pos;
+    P.has_aov = (P.aov.state || P.aov.voxel || P.aov.leaf || P.aov.level || P.aov.iters || P.aov.depth || P.aov.mask || P.aov.pos) ? 1u : 0u;
+  }
+  if (n_states == 1) {
+    P.s0 = states[0];
+  } else {
+    if (s.states_cap < n_states) {
+      if (s.d_states) (void)cudaFree(s.d_states);
+      s.d_states = nullptr, s.states_cap = 0;
+      WX_CUDA(ctx, cudaMalloc(&s.d_states, (size_t)n_states * sizeof(WxState)));
+      s.states_cap = n_states;
+    }
+    WX_CUDA(ctx, cudaMemcpyAsync(s.d_states, states, (size_t)n_states * sizeof(WxState), cudaMemcpyHostToDevice, stream));
+    P.states = s.d_states;
+  }
+  uint32_t total_launches = 0;
+  // a camera batch is launched per run of equal render modes (normally one run)
+  for (uint32_t b = 0; b < n_states;) {
+    uint32_t e = b + 1;
+    const uint32_t mode = states[b].render_mode[0] > 4 ? 0 : states[b].render_mode[0];
+    while (e < n_states && (states[e].render_mode[0] > 4 ? 0 : states[e].render_mode[0]) == mode) ++e;
+    P.cam_base = b;
+    if (shard) P.shard_index = shard->index, P.shard_count = shard->count, P.band_rows = shard->band_rows;
+    else P.shard_index = 0, P.shard_count = 1, P.band_rows = 0;
+    uint32_t l = 0;
+    WX_CUDA(ctx, launch_raycast(P, e - b, mode, stream, &l));
+    total_launches += l;
+    b = e;
+  }
+  *launches_out = total_launches;
+  return WX_OK;
+}
+
+static int check_render_args(WxContext* ctx, const WxTree* tree, const WxState* states, uint32_t n_states, uint32_t width,
+                             uint32_t height, const void* rgba) {
+  if (!ctx || !tree || !states || !rgba) return fail(ctx, WX_ERR_INVALID_ARGUMENT, "render: null argument");
+  if (tree->ctx != ctx) return fail(ctx, WX_ERR_INVALID_ARGUMENT, "render: tree belongs to another context");
+  if (n_states == 0 || width == 0 || height == 0) return fail(ctx, WX_ERR_INVALID_ARGUMENT, "render: empty frame");
+  if ((uint64_t)width * height * n_states > (1ull << 40)) return fail(ctx, WX_ERR_INVALID_ARGUMENT, "render: frame too large");
+  return WX_OK;
+}
+
+extern "C" int wx_render_device(WxContext* ctx, int device_index, const WxTree* tree, const WxState* states, uint32_t n_states,
+                                uint32_t width, uint32_t height, uint8_t* rgba_dev, const WxAov* aov_dev, const WxShard* shard,
+                                void* stream) {
+  int rc = check_render_args(ctx, tree, states, n_states, width, height, rgba_dev);
+  if (rc) return rc;
+  if (device_index < 0 || device_index >= (int)ctx->dev.size()) return fail(ctx, WX_ERR_INVALID_ARGUMENT, "render: device index");
+  if (shard && (shard->count == 0 || shard->index >= shard->count ||
+                (shard->count > 1 && (shard->band_rows == 0 || shard->band_rows % kBandRowsMultiple != 0))))
+    return fail(ctx, WX_ERR_INVALID_ARGUMENT, "render: bad shard (band_rows must be a positive multiple of 8)");
+  DeviceSlot& s = ctx->dev[device_index];
+  WX_CUDA(ctx, cudaSetDevice(s.id));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  WX_CUDA(ctx, cudaEventRecord(s.ev0, st));
+  uint32_t launches = 0;
+  rc = launch_on(ctx, device_index, tree, states, n_states, width, height, rgba_dev, aov_dev, shard, st, &launches);
+  if (rc) return rc;
+  WX_CUDA(ctx, cudaEventRecord(s.ev1, st));
+  for (DeviceSlot& d : ctx->dev) d.events_pending = false;
+  s.events_pending = true;
+  ctx->total_pending = false;
+  ctx->info = WxRenderInfo{};
+  ctx->info.launches = launches;
+  ctx->info.rays = (uint64_t)(width / 8 * 8) * (height / 4 * 4) * n_states;  // whole frame; a shard renders its share
+  return WX_OK;
+}
+
+static int ensure(WxContext* ctx, void** p, size_t* have, size_t need) {
+  if (*have >= need) return WX_OK;
+  if (*p) (void)cudaFree(*p);
+  *p = nullptr, *have = 0;
+  WX_CUDA(ctx, cudaMalloc(p, need));
+  *have = need;
+  return WX_OK;
+}
+
+extern "C" int wx_render(WxContext* ctx, const WxTree* tree, const WxState* states, uint32_t n_states, uint32_t width,
+                         uint32_t height, uint8_t* rgba_out, const WxAov* aov_out) {
+  int rc = check_render_args(ctx, tree, states, n_states, width, height, rgba_out);
+  if (rc) return rc;
+  const size_t npix = (size_t)n_states * width * height;
+  DeviceSlot& d0 = ctx->dev[0];
+  WX_CUDA(ctx, cudaSetDevice(d0.id));
+  rc = ensure(ctx, (void**)&ctx->fb.rgba, &ctx->fb.rgba_bytes, npix * 4);
+  if (rc) return rc;
+  // AOV staging on device 0
+  static const size_t aov_elem[8] = {1, 12, 4, 1, 4, 4, 1, 12};
+  void* host_aov[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  WxAov dev_aov;
+  memset(&dev_aov, 0, sizeof(dev_aov));
+  bool any_aov = false;
+  if (aov_out) {
+    host_aov[0] = aov_out->state, host_aov[1] = aov_out->voxel, host_aov[2] = aov_out->leaf, host_aov[3] = aov_out->level;
+    host_aov[4] = aov_out->iters, host_aov[5] = aov_out->depth, host_aov[6] = aov_out->mask, host_aov[7] = aov_out->pos;
+    for (int k = 0; k < 8; ++k) {
+      if (!host_aov[k]) continue;
+      any_aov = true;
+      rc = ensure(ctx, &ctx->fb.aov[k], &ctx->fb.aov_bytes[k], npix * aov_elem[k]);
+      if (rc) return rc;
+    }
+    dev_aov.state = host_aov[0] ? (uint8_t*)ctx->fb.aov[0] : nullptr;
+    dev_aov.voxel = host_aov[1] ? (int32_t*)ctx->fb.aov[1] : nullptr;
+    dev_aov.leaf = host_aov[2] ? (int32_t*)ctx->fb.aov[2] : nullptr;
+    dev_aov.level = host_aov[3] ? (uint8_t*)ctx->fb.aov[3] : nullptr;
+    dev_aov.iters = host_aov[4] ? (uint32_t*)ctx->fb.aov[4] : nullptr;
+    dev_aov.depth = host_aov[5] ? (float*)ctx->fb.aov[5] : nullptr;
+    dev_aov.mask = host_aov[6] ? (uint8_t*)ctx->fb.aov[6] : nullptr;
+    dev_aov.pos = host_aov[7] ? (float*)ctx->fb.aov[7] : nullptr;
+  }
+
+  const int ndev = (int)ctx->dev.size();
+  WX_CUDA(ctx, cudaEventRecord(ctx->total0, d0.stream));
+  uint32_t launches = 0;
+  if (ndev == 1) {
+    WX_CUDA(ctx, cudaEventRecord(d0.ev0, d0.stream));
+    rc = launch_on(ctx, 0, tree, states, n_states, width, height, ctx->fb.rgba, any_aov ? &dev_aov : nullptr, nullptr, d0.stream, &launches);
+    if (rc) return rc;
+    WX_CUDA(ctx, cudaEventRecord(d0.ev1, d0.stream));
+    d0.events_pending = true;
+  } else {
+    // Row bands of one tile height, dealt round-robin: every GPU gets hit-heavy and empty regions.
+    // Each GPU stores its pixels straight into device 0's frame over NVLink (the store is the gather).
+    for (int i = 0; i < ndev; ++i) {
+      DeviceSlot& s = ctx->dev[i];
+      WX_CUDA(ctx, cudaSetDevice(s.id));
+      WxShard sh{(uint32_t)i, (uint32_t)ndev, (uint32_t)kBandRowsMultiple, 0};
+      uint8_t* dst = ctx->fb.rgba;
+      const bool direct = (i == 0) || s.peer_to_first;
+      if (!direct) {
+        if (any_aov) return fail(ctx, WX_ERR_PEER_ACCESS, "wx_render: AOVs on several devices need peer access to device 0");
+        rc = ensure(ctx, (void**)&s.scratch, &s.scratch_bytes, npix * 4);
+        if (rc) return rc;
+        dst = s.scratch;
+      }
+      WX_CUDA(ctx, cudaEventRecord(s.ev0, s.stream));
+      uint32_t l = 0;
+      rc = launch_on(ctx, i, tree, states, n_states, width, height, dst, any_aov ? &dev_aov : nullptr, &sh, s.stream, &l);
+      if (rc) return rc;
+      launches += l;
+      WX_CUDA(ctx, cudaEventRecord(s.ev1, s.stream));
+      s.events_pending = true;
+      if (!direct) {  // staged gather: copy this GPU's bands into device 0's frame
+        const size_t band_bytes = (size_t)kBandRowsMultiple * width * 4;
+        const uint32_t bands = (height + kBandRowsMultiple - 1) / kBandRowsMultiple;
+        for (uint32_t c = 0; c < n_states; ++c)
+          for (uint32_t b = (uint32_t)i; b < bands; b += (uint32_t)ndev) {
+            const size_t off = ((size_t)c * height + (size_t)b * kBandRowsMultiple) * width * 4;
+            const size_t bytes = std::min(band_bytes, ((size_t)(c + 1) * height * width * 4) - off);
+            WX_CUDA(ctx, cudaMemcpyPeerAsync(ctx->fb.rgba + off, d0.id, s.scratch + off, s.id, bytes, s.stream));
+          }
+      }
+    }
+    for (int i = 1; i < ndev; ++i) {  // device 0's stream waits for the peers' stores
+      WX_CUDA(ctx, cudaSetDevice(ctx->dev[i].id));
+      cudaEvent_t done;
+      WX_CUDA(ctx, cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
+      WX_CUDA(ctx, cudaEventRecord(done, ctx->dev[i].stream));
+      WX_CUDA(ctx, cudaSetDevice(d0.id));
+      WX_CUDA(ctx, cudaStreamWaitEvent(d0.stream, done, 0));
+      WX_CUDA(ctx, cudaEventDestroy(done));
+    }
+    WX_CUDA(ctx, cudaSetDevice(d0.id));
+  }
+  WX_CUDA(ctx, cudaMemcpyAsync(rgba_out, ctx->fb.rgba, npix * 4, cudaMemcpyDeviceToHost, d0.stream));
+  for (int k = 0; k < 8; ++k)
+    if (host_aov[k]) WX_CUDA(ctx, cudaMemcpyAsync(host_aov[k], ctx->fb.aov[k], npix * aov_elem[k], cudaMemcpyDeviceToHost, d0.stream));
+  WX_CUDA(ctx, cudaEventRecord(ctx->total1, d0.stream));
+  WX_CUDA(ctx, cudaStreamSynchronize(d0.stream));
+  ctx->total_pending = true;
+  ctx->info = WxRenderInfo{};
+  ctx->info.launches = launches;
+  ctx->info.rays = (uint64_t)(width / 8 * 8) * (height / 4 * 4) * n_states;
+  return WX_OK;
+}
+
+extern "C" int wx_last_render_info(const WxContext* cctx, WxRenderInfo* info) {
+  WxContext* ctx = const_cast<WxContext*>(cctx);
+  if (!ctx || !info) return WX_ERR_INVALID_ARGUMENT;
+  float kmax = 0.f;
+  for (DeviceSlot& s : ctx->dev) {
+    if (!s.events_pending) continue;
+    WX_CUDA(ctx, cudaSetDevice(s.id));
+    WX_CUDA(ctx, cudaEventSynchronize(s.ev1));
+    float ms = 0.f;
+    WX_CUDA(ctx, cudaEventElapsedTime(&ms, s.ev0, s.ev1));
+    kmax = std::max(kmax, ms);
+  }
+  ctx->info.kernel_ms = kmax;
+  if (ctx->total_pending) {
+    WX_CUDA(ctx, cudaSetDevice(ctx->dev[0].id));
+    WX_CUDA(ctx, cudaEventSynchronize(ctx->total1));
+    float ms = 0.f;
+    WX_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->total0, ctx->total1));
+    ctx->info.total_ms = ms;
+  }
+  (void)cudaSetDevice(ctx->dev[0].id);
+  *info = ctx->info;
+  return WX_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Memory helpers
+// ---------------------------------------------------------------------------------------------
+static int slot_of(WxContext* ctx, int device_index, DeviceSlot** s) {
+  if (!ctx || device_index < 0 || device_index >= (int)ctx->dev.size()) return fail(ctx, WX_ERR_INVALID_ARGUMENT, "bad device index");
+  *s = &ctx->dev[device_index];
+  WX_CUDA(ctx, cudaSetDevice((*s)->id));
+  return WX_OK;
+}
+
+extern "C" int wx_device_alloc(WxContext* ctx, int device_index, size_t bytes, void** out) {
+  DeviceSlot* s;
+  if (!out) return WX_ERR_INVALID_ARGUMENT;
+  int rc = slot_of(ctx, device_index, &s);
+  if (rc) return rc;
+  WX_CUDA(ctx, cudaMalloc(out, bytes ? bytes : 1));
+  return WX_OK;
+}
+extern "C" int wx_device_free(WxContext* ctx, int device_index, void* ptr) {
+  DeviceSlot* s;
+  int rc = slot_of(ctx, device_index, &s);
+  if (rc) return rc;
+  WX_CUDA(ctx, cudaFree(ptr));
+  return WX_OK;
+}
+extern "C" int wx_host_alloc_pinned(size_t bytes, void** out) {
+  if (!out) return WX_ERR_INVALID_ARGUMENT;
+  cudaError_t e = cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable);
+  if (e != cudaSuccess) return fail_cuda(nullptr, e, "cudaHostAlloc");
+  return WX_OK;
+}
+extern "C" int wx_host_free_pinned(void* ptr) {
+  cudaError_t e = cudaFreeHost(ptr);
+  if (e != cudaSuccess) return fail_cuda(nullptr, e, "cudaFreeHost");
+  return WX_OK;
+}
+extern "C" int wx_memcpy_d2h(WxContext* ctx, int device_index, void* dst_host, const void* src_dev, size_t bytes, void* stream) {
+  DeviceSlot* s;
+  int rc = slot_of(ctx, device_index, &s);
+  if (rc) return rc;
+  WX_CUDA(ctx, cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, reinterpret_cast<cudaStream_t>(stream)));
+  return WX_OK;
+}
+extern "C" int wx_stream_synchronize(WxContext* ctx, int device_index, void* stream) {
+  DeviceSlot* s;
+  int rc = slot_of(ctx, device_index, &s);
+  if (rc) return rc;
+  WX_CUDA(ctx, cudaStreamSynchronize(reinterpret_cast<cudaStream_t>(stream)));
+  return WX_OK;
+}
+extern "C" int wx_ipc_export(WxContext* ctx, int device_index, void* ptr, uint8_t handle_out[64]) {
+  DeviceSlot* s;
+  int rc = slot_of(ctx, device_index, &s);
+  if (rc) return rc;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "ipc handle size");
+  cudaIpcMemHandle_t h;
+  WX_CUDA(ctx, cudaIpcGetMemHandle(&h, ptr));
+  memcpy(handle_out, &h, 64);
+  return WX_OK;
+}
+extern "C" int wx_ipc_open(WxContext* ctx, int device_index, const uint8_t handle[64], void** out) {
+  DeviceSlot* s;
+  if (!out) return WX_ERR_INVALID_ARGUMENT;
+  int rc = slot_of(ctx, device_index, &s);
+  if (rc) return rc;
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, 64);
+  WX_CUDA(ctx, cudaIpcOpenMemHandle(out, h, cudaIpcMemLazyEnablePeerAccess));
+  return WX_OK;
+}
+extern "C" int wx_ipc_close(WxContext* ctx, int device_index, void* ptr) {
+  DeviceSlot* s;
+  int rc = slot_of(ctx, device_index, &s);
+  if (rc) return rc;
+  WX_CUDA(ctx, cudaIpcCloseMemHandle(ptr));
+  return WX_OK;
+}

@@ -1,0 +1,98 @@
+// wx_raycast.cu -- the raycast kernels (cp_main of the reference, src/shaders/raycast.comp.wgsl:60-68)
+// and their launcher.  One thread per primary ray; a warp is an 8x4 pixel tile (the reference's
+// workgroup shape, so that the rays of a warp walk the same nodes); a CTA is 2x2 such tiles.
+#include "wx_device.cuh"
+#include "wx_internal.h"
+
+namespace wx {
+
+constexpr int kTileW = 16, kTileH = 8;  // CTA footprint in pixels
+constexpr int kThreads = 128;
+
+template <int MODE, bool AOV>
+__global__ void __launch_bounds__(kThreads) raycast_kernel(const __grid_constant__ RenderParams P) {
+  // ---- pixel of this thread ------------------------------------------------------------------
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t tx = blockIdx.x % P.tiles_x;
+  const uint32_t trow = blockIdx.x / P.tiles_x;                 // tile row among the rows this launch owns
+  const uint32_t band = (trow / P.tile_rows_per_band) * P.shard_count + P.shard_index;
+  const uint32_t x = tx * kTileW + (warp & 1) * 8 + (lane & 7);
+  const uint32_t y = band * P.band_rows + (trow % P.tile_rows_per_band) * kTileH + (warp >> 1) * 4 + (lane >> 3);
+  const uint32_t cam = P.cam_base + blockIdx.y;
+  if (x >= P.width || y >= P.height) return;
+  const size_t pix = ((size_t)cam * P.height + y) * P.width + x;
+  if (x >= P.disp_w || y >= P.disp_h) {  // never dispatched by the reference: zero-initialised texel
+    P.rgba[pix] = make_uchar4(0, 0, 0, 0);
+    return;
+  }
+  const WxState& s = (P.n_states == 1) ? P.s0 : P.states[cam];
+
+  // ---- cp_main -------------------------------------------------------------------------------
+  const float px = (float)x + 0.001f, py = (float)y + 0.001f;
+  const V3 u = V3{s.u[0], s.u[1], s.u[2]}, mv = V3{s.mv[0], s.mv[1], s.mv[2]}, wp = V3{s.wp[0], s.wp[1], s.wp[2]};
+  const V3 eye = V3{s.eye[0], s.eye[1], s.eye[2]};
+  const V3 dir = normalize3((px * u + py * mv) + wp);
+
+  const HitOut hit = hdda_ray(P.tree, eye, dir);
+  const V3 col = shade<MODE>(P.tree, s, hit, dir);
+  P.rgba[pix] = make_uchar4((unsigned char)unorm8(col.x), (unsigned char)unorm8(col.y), (unsigned char)unorm8(col.z), 255);
+
+  if (AOV) {
+    const AovPtrs& a = P.aov;
+    if (a.state) a.state[pix] = (uint8_t)hit.state;
+    if (a.voxel) {
+      a.voxel[3 * pix + 0] = __float2int_rd(hit.p.x);
+      a.voxel[3 * pix + 1] = __float2int_rd(hit.p.y);
+      a.voxel[3 * pix + 2] = __float2int_rd(hit.p.z);
+    }
+    if (a.leaf) a.leaf[pix] = hit.level == 3u ? (int32_t)hit.n3 : -1;
+    if (a.level) a.level[pix] = (uint8_t)hit.level;
+    if (a.iters) a.iters[pix] = hit.i;
+    if (a.depth) {
+      const V3 d = hit.p - eye;
+      a.depth[pix] = sqrtf(dot3(d, d));
+    }
+    if (a.mask) a.mask[pix] = (uint8_t)hit.mask;
+    if (a.pos) a.pos[3 * pix + 0] = hit.p.x, a.pos[3 * pix + 1] = hit.p.y, a.pos[3 * pix + 2] = hit.p.z;
+  }
+}
+
+template <int MODE>
+static cudaError_t launch_mode(const RenderParams& P, dim3 grid, cudaStream_t stream) {
+  if (P.has_aov) raycast_kernel<MODE, true><<<grid, kThreads, 0, stream>>>(P);
+  else raycast_kernel<MODE, false><<<grid, kThreads, 0, stream>>>(P);
+  return cudaGetLastError();
+}
+
+// Fills the launch geometry of P (shard -> bands -> tile rows) and launches frames
+// [P.cam_base, P.cam_base + n_cams) in render mode `render_mode` (the caller groups a camera batch
+// by mode).  P.n_states is the total number of states behind P.states / P.s0.
+cudaError_t launch_raycast(RenderParams& P, uint32_t n_cams, uint32_t render_mode, cudaStream_t stream, uint32_t* launches) {
+  *launches = 0;
+  if (P.shard_count == 0) P.shard_count = 1, P.shard_index = 0;
+  if (P.band_rows == 0 || P.shard_count == 1) {
+    // a single shard owns every row: one band as tall as the frame (rounded up to the tile height)
+    P.band_rows = ((P.height + kTileH - 1) / kTileH) * kTileH;
+    P.shard_count = 1, P.shard_index = 0;
+  }
+  const uint32_t total_bands = (P.height + P.band_rows - 1) / P.band_rows;
+  P.own_bands = total_bands > P.shard_index ? (total_bands - P.shard_index + P.shard_count - 1) / P.shard_count : 0;
+  P.tiles_x = (P.width + kTileW - 1) / kTileW;
+  P.tile_rows_per_band = P.band_rows / kTileH;
+  P.disp_w = (P.width / 8) * 8;
+  P.disp_h = (P.height / 4) * 4;
+  if (P.own_bands == 0 || n_cams == 0 || P.tiles_x == 0) return cudaSuccess;
+  const uint64_t blocks = (uint64_t)P.tiles_x * P.tile_rows_per_band * P.own_bands;
+  if (blocks > 0x7fffffffull || n_cams > 65535u) return cudaErrorInvalidConfiguration;
+  dim3 grid((unsigned)blocks, n_cams, 1);
+  *launches = 1;
+  switch (render_mode) {
+    case 1: return launch_mode<1>(P, grid, stream);
+    case 2: return launch_mode<2>(P, grid, stream);
+    case 3: return launch_mode<3>(P, grid, stream);
+    case 4: return launch_mode<4>(P, grid, stream);
+    default: return launch_mode<0>(P, grid, stream);  // Gray and the shader's `default:` arms
+  }
+}
+
+}  // namespace wx
