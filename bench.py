@@ -1,0 +1,392 @@
+#!/usr/bin/env python
+"""bench.py -- primary Mrays/s of the raycast hot path on N B200s (one process per GPU) + roofline + CPU baseline.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--scene sphere2048|cube|icosahedron|sphere256]
+  N > 1:  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+A "step" is one pass of the hot path over one batch of rays: every rank renders one 3840x2160 frame
+(render mode 0 = Gray: exactly one hdda_ray per pixel) of the procedural 2048^3 sphere level set
+(BASELINE.json config 3, the configuration the north-star target is quoted on).  Rank r looks from
+orbit camera r (camera 0 is config 3's camera; the sphere makes every orbit view the same workload),
+so per-GPU work is fixed as N grows ("scaling": "weak", BASELINE config 5's camera sharding).  For
+N > 1 every rank's kernel stores its pixels straight into one frame stack on GPU 0 through a CUDA-IPC
+peer mapping (the final store IS the NVLink gather; no separate collective on the data path).
+
+Timing: W warm-up steps, then K steps between barrier+synchronize brackets; the device time of every
+step is taken with CUDA events on the launching stream, L2 is flushed (256 MiB write) before every
+timed step outside the event pair, and the per-step times are reduced with MAX over ranks.
+`e2e` goes through wx_render with HOST buffers: state H2D + kernel + RGBA D2H into pinned memory.
+
+The oracle (oracle/, a CPU restatement of the reference shader) is used here only for the reported
+`cpu_baseline` and for `--impl reference`; the reference itself (Rust + wgpu) cannot run in this image.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "tests")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np  # noqa: E402
+
+WIDTH, HEIGHT = 3840, 2160
+METRIC = "primary Mrays/s per frame"
+UNIT = "Mrays/s"
+
+
+# ------------------------------------------------------------------------------------------------
+# workload
+# ------------------------------------------------------------------------------------------------
+def orbit_eye(k: int, n: int = 64, radius: float = 2500.0, elevation_deg: float = 0.0):
+    """Camera k of an orbit around +y through config 3's eye (k = 0 -> (0.5, 0.5, -2500.5))."""
+    th = 2.0 * math.pi * k / n
+    el = math.radians(elevation_deg)
+    r = radius + 1.0  # centre (0.5,0.5,0.5) + 2501 * direction: k = 0 gives exactly (0.5, 0.5, -2500.5)
+    return (0.5 + r * math.cos(el) * math.sin(th), 0.5 + r * math.sin(el), 0.5 - r * math.cos(el) * math.cos(th))
+
+
+def build_scene(name: str):
+    """Returns (VDB345 with SDF, FlatTree u32, description string).  Product host code only."""
+    import woxel_b200 as W
+    import scenes
+    t0 = time.time()
+    if name == "sphere2048":
+        v = W.VDB345.sphere(half=1024, radius=1000.0, band=3.0)
+        what = "procedural 2048^3 sphere level set (R=1000, band +-3)"
+    elif name == "sphere256":
+        v = W.VDB345.sphere(half=128, radius=100.0, band=2.0)
+        what = "procedural 256^3 sphere level set (R=100, band +-2) [debug size]"
+    elif name in ("cube", "icosahedron"):
+        t = scenes.load_topo(name)
+        v = None
+        what = f"assets/{name}.vdb topology (tests/golden/{name}.topo.npz)"
+    else:
+        raise SystemExit(f"unknown scene {name}")
+    if v is None:
+        # rebuild the asset in the product tree from the golden topology
+        v = scenes.host_tree_from_scene(_TopoView(t))
+    t1 = time.time()
+    v.compute_sdf()
+    t2 = time.time()
+    flat = v.to_flat(narrow_leaves=False)
+    return v, flat, what, {"build_s": round(t1 - t0, 2), "sdf_s": round(t2 - t1, 2), "flat_s": round(time.time() - t2, 2)}
+
+
+class _TopoView:
+    def __init__(self, t):
+        self.origins, self.kids5, self.vals5, self.kids4, self.vals4, self.vals3 = (t[k] for k in ("origins", "kids5", "vals5", "kids4", "vals4", "vals3"))
+
+
+def camera_for(scene: str, k: int):
+    if scene.startswith("sphere2048"):
+        return orbit_eye(k), (0.5, 0.5, 0.5)
+    if scene == "sphere256":
+        return (0.5, 0.5, -300.5), (0.5, 0.5, 0.5)
+    return (0.5, 0.5, -500.5), (0.5, 0.5, -498.5)
+
+
+def make_state(scene: str, k: int):
+    import woxel_b200 as W
+    eye, target = camera_for(scene, k)
+    return W.ComputeState.build(W.Camera(eye=eye, target=target, aspect=WIDTH / HEIGHT), WIDTH, W.RenderMode.Gray)
+
+
+def oracle_gpudata(flat):
+    import oracle_ffi as O
+    return O.gpudata_from_tables(flat.origins, flat.kids5, flat.vals5, flat.tab5, flat.kids4, flat.vals4, flat.tab4, flat.vals3, flat.tab3)
+
+
+def oracle_state(ws):
+    import oracle_ffi as O
+    return O.State.from_buffer_copy(bytes(ws))
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.rows = []
+        self.proc = None
+        self.gpu_index = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+            except Exception:
+                continue
+            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
+                if len(r) > col and r[col].lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm: the oracle port on the host cores
+# ------------------------------------------------------------------------------------------------
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import __graft_entry__ as g
+    g.build()
+    _, flat, what, prep = build_scene(args.scene)
+    gd = oracle_gpudata(flat)
+    st = oracle_state(make_state(args.scene, 0))
+    cores = os.cpu_count() or 1
+    # bounded sample: every 8th band of 8 rows (1/8 of the frame, spread over hits and misses alike)
+    bands = [b for b in range(HEIGHT // 8) if b % 8 == 0]
+    rays_per_step = len(bands) * 8 * WIDTH
+
+    def step():
+        for b in bands:
+            gd.render(st, WIDTH, HEIGHT, aov=False, threads=cores, rows=(8 * b, 8 * b + 8))
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    value = rays_per_step * args.steps / dt / 1e6
+    sample = f"every 8th band of 8 rows of the {WIDTH}x{HEIGHT} frame ({rays_per_step} rays/step), {cores} threads"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": round(1e3 * dt / args.steps, 3), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{what}, {WIDTH}x{HEIGHT}, render mode 0 (Gray), camera 0", "note":
+                   "reference arm = CPU restatement (oracle/) of raycast.comp.wgsl on the host cores; the Rust/wgpu reference "
+                   "cannot be built or run in this image (no rustc, wgpu, Vulkan ICD)"},
+        "cpu_baseline": {"value": round(value, 3), "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": round(value, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--scene", default="sphere2048")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as g
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if rank == 0:
+        g.build()  # no-op when the in-tree .so files are current
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the raycast path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist.barrier()
+    import woxel_b200 as W
+    from woxel_b200 import _ffi
+    lib = _ffi.cuda_lib()
+
+    v, flat, what, prep = build_scene(args.scene)
+    ctx = W.Context()  # current device
+    tree = ctx.upload(flat)
+    state = make_state(args.scene, rank)
+    frame_bytes = WIDTH * HEIGHT * 4
+    rays_per_frame = (WIDTH // 8 * 8) * (HEIGHT // 4 * 4)
+
+    # ---- frame stack on GPU 0; peers map it through CUDA IPC -----------------------------------
+    stack = C.c_void_p()
+    if rank == 0:
+        ctx.check(lib.wx_device_alloc(ctx._h, 0, frame_bytes * world, C.byref(stack)))
+    if world > 1:
+        handle = (C.c_uint8 * 64)()
+        if rank == 0:
+            ctx.check(lib.wx_ipc_export(ctx._h, 0, stack, handle))
+        objs = [bytes(handle) if rank == 0 else None]
+        dist.broadcast_object_list(objs, src=0)
+        if rank != 0:
+            h = (C.c_uint8 * 64).from_buffer_copy(objs[0])
+            ctx.check(lib.wx_ipc_open(ctx._h, 0, h, C.byref(stack)))
+    my_frame = stack.value + rank * frame_bytes
+
+    stream = torch.cuda.current_stream()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def step(timed_events=None):
+        flush.fill_(1)  # evict L2 (126 MB) between steps; outside the event pair
+        if timed_events is not None:
+            timed_events[0].record(stream)
+        ctx.render_device(tree, state, WIDTH, HEIGHT, my_frame, stream=stream.cuda_stream)
+        if timed_events is not None:
+            timed_events[1].record(stream)
+
+    for _ in range(args.warmup):
+        step()
+    sync_all()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    sync_all()
+    t_wall0 = time.perf_counter()
+    for k in range(args.steps):
+        step(evs[k])
+    sync_all()
+    wall = time.perf_counter() - t_wall0
+    ms = torch.tensor([a.elapsed_time(b) for a, b in evs], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)  # per-step max over ranks
+    ms = ms.cpu().numpy()
+    ms_per_step = float(ms.sum() / args.steps)
+    value = world * rays_per_frame / (ms_per_step * 1e-3) / 1e6
+
+    # warm-L2 figure (no flush), for reference only
+    for _ in range(3):
+        ctx.render_device(tree, state, WIDTH, HEIGHT, my_frame, stream=stream.cuda_stream)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync_all()
+    e0.record(stream)
+    for _ in range(10):
+        ctx.render_device(tree, state, WIDTH, HEIGHT, my_frame, stream=stream.cuda_stream)
+    e1.record(stream)
+    sync_all()
+    warm_ms = torch.tensor([e0.elapsed_time(e1) / 10], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(warm_ms, op=dist.ReduceOp.MAX)
+    warm_ms = float(warm_ms.item())
+
+    # ---- e2e: the public host-buffer call (state H2D, kernel, RGBA D2H into pinned memory) ------
+    pinned = C.c_void_p()
+    ctx.check(lib.wx_host_alloc_pinned(frame_bytes, C.byref(pinned)))
+    host_frame = np.frombuffer((C.c_uint8 * frame_bytes).from_address(pinned.value), np.uint8).reshape(1, HEIGHT, WIDTH, 4)
+    for _ in range(3):
+        ctx.render(tree, state, WIDTH, HEIGHT, out=host_frame)
+    sync_all()
+    e2e_steps = max(5, min(args.steps, 20))
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        ctx.render(tree, state, WIDTH, HEIGHT, out=host_frame)  # blocking
+    e2e_dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(e2e_dt, op=dist.ReduceOp.MAX)
+    e2e_value = world * rays_per_frame * e2e_steps / float(e2e_dt.item()) / 1e6
+    checksum = int(host_frame.view(np.uint32).sum(dtype=np.uint64))
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- rank 0: CPU baseline + roofline ----------------------------------------------------------
+    if rank == 0:
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
+        else:
+            peak, peak_src = 6650.0, "B200_PROFILING.md fallback (of fallback)"
+        cpu_baseline, bytes_per_ray, steps_per_ray, parity = None, None, None, None
+        if not args.no_cpu_baseline and world == 1:
+            gd = oracle_gpudata(flat)
+            cores = os.cpu_count() or 1
+            t0 = time.perf_counter()
+            ref_rgba, _, st = gd.render(oracle_state(state), WIDTH, HEIGHT, aov=False, threads=cores)
+            dt = time.perf_counter() - t0
+            cpu_baseline = {"value": round(st.primary_rays / dt / 1e6, 3), "unit": UNIT, "cores": cores, "kind": "port",
+                            "sample": f"one full {WIDTH}x{HEIGHT} frame of the same scene/camera/mode ({st.primary_rays} rays), "
+                                      f"oracle/ C restatement of raycast.comp.wgsl, {cores} threads, {dt:.2f} s"}
+            bytes_per_ray = st.primary_alg_bytes / st.primary_rays
+            steps_per_ray = sum(st.primary_lookups) / st.primary_rays
+            parity = bool(np.array_equal(ref_rgba, host_frame[0]))
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get(args.scene, {}).get("dram_bytes_per_launch")
+        roof = None
+        if bytes_per_ray is not None:
+            achieved = bytes_per_ray * rays_per_frame / (ms_per_step * 1e-3) / 1e9
+            roof = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
+                    "traffic": traffic, "peak_source": peak_src, "kernel": "wx::raycast_kernel<0,false>",
+                    "alg_bytes_per_ray": round(bytes_per_ray, 2), "lookups_per_ray": round(steps_per_ray, 2),
+                    "rays_per_launch": rays_per_frame,
+                    "note": "algorithmic bytes (SURVEY 8d) over the CUDA-event time of the kernel, L2 flushed before each launch; "
+                            "the working set is L2-resident so this is a bandwidth-equivalent figure, the kernel is latency/issue bound"}
+        out = {
+            "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{what}, {WIDTH}x{HEIGHT}, render mode 0 (Gray, 1 hdda_ray/pixel), one frame per GPU per step "
+                                   f"(orbit camera = rank), frames stored into GPU0 over NVLink when N>1",
+                       "l2": "flushed (256 MiB fill) before every timed step; value_warm_l2 is the same loop without the flush",
+                       "tree": {"n5": tree.info.n5, "n4": tree.info.n4, "n3": tree.info.n3, "leaf_bits": tree.info.leaf_bits,
+                                "device_MB": round(tree.info.device_bytes / 1e6, 1)},
+                       "prep_s": prep},
+            "value_warm_l2": round(world * rays_per_frame / (warm_ms * 1e-3) / 1e6, 1),
+            "wall_ms_per_step_incl_flush": round(1e3 * wall / args.steps, 4),
+            "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": 256 * world, "d2h_bytes_per_step": frame_bytes * world,
+                    "api": "wx_render (host state in, pinned host RGBA8 out), blocking", "steps": e2e_steps},
+            "gpu_launches": args.steps * world,
+            "clocks": clocks, "roofline": roof, "cpu_baseline": cpu_baseline,
+            "parity_vs_oracle_full_frame": parity, "frame_checksum": checksum,
+        }
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        if rank != 0:
+            lib.wx_ipc_close(ctx._h, 0, stack)
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
