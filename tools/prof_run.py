@@ -27,7 +27,12 @@ st.render_mode[0] = a.mode
 lib = _ffi.cuda_lib()
 buf = C.c_void_p()
 ctx.check(lib.wx_device_alloc(ctx._h, 0, bench.WIDTH * bench.HEIGHT * 4, C.byref(buf)))
+ms = []
 for _ in range(a.frames):
     ctx.render_device(tree, st, bench.WIDTH, bench.HEIGHT, buf.value)
     ctx.check(lib.wx_stream_synchronize(ctx._h, 0, None))
-    print("frame", ctx.last_render_info().kernel_ms, "ms")
+    ms.append(ctx.last_render_info().kernel_ms)
+rays = (bench.WIDTH // 8 * 8) * (bench.HEIGHT // 4 * 4)
+best = sorted(ms[1:])[len(ms[1:]) // 2] if len(ms) > 1 else ms[0]
+print("lib", os.environ.get("WOXEL_B200_LIB", "default"), "scene", a.scene, "mode", a.mode, "median_ms", round(best, 4),
+      "Mrays/s", round(rays / best / 1e3, 1), "all_ms", [round(m, 3) for m in ms])

@@ -50,14 +50,17 @@ struct WxContext {
 };
 
 struct TreeOnDevice {
-  uint32_t *e5 = nullptr, *e4 = nullptr, *l3 = nullptr;
+  uint32_t *e5 = nullptr, *e4 = nullptr;
+  uint8_t* l3 = nullptr;
   int4* origins = nullptr;
 };
 
 struct WxTree {
   WxContext* ctx = nullptr;
   std::vector<TreeOnDevice> on;  // one per context device
-  std::vector<int4> origins;
+  std::vector<int4> origins;  // biased by kBias (wx_device.cuh)
+  uint32_t leaf_shift = 9;    // log2(bytes per leaf brick)
+  bool fast_ok = true;        // every step size < 2^20: the fast march applies
   WxTreeInfo info{};
 };
 
@@ -207,9 +210,16 @@ static void parallel_for(size_t n, F&& f) {
 
 static inline bool bit(const uint64_t* m, size_t i) { return (m[i >> 6] >> (i & 63)) & 1ull; }
 
+static inline uint32_t float_bits(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  return u;
+}
+
 // One internal level.  Returns 0, or a negative status; *max_dist receives the largest tile distance.
-static int pack_internal(uint32_t n_nodes, uint32_t slots, const uint64_t* kids, const uint64_t* vals, const uint32_t* tab,
-                         uint32_t n_children, std::vector<uint32_t>& out, uint32_t* max_dist) {
+// A tile entry is the f32 bit pattern of f32(dist) * cell, the `size` of raycast.comp.wgsl:104.
+static int pack_internal(uint32_t n_nodes, uint32_t slots, float cell, const uint64_t* kids, const uint64_t* vals,
+                         const uint32_t* tab, uint32_t n_children, std::vector<uint32_t>& out, uint32_t* max_dist) {
   out.assign((size_t)n_nodes * slots, 0u);
   std::atomic<int> status{0};
   std::atomic<uint32_t> mx{0};
@@ -233,7 +243,7 @@ static int pack_internal(uint32_t n_nodes, uint32_t slots, const uint64_t* kids,
           status.store(WX_ERR_UNSUPPORTED);
           return;
         }
-        o[s] = t[s];
+        o[s] = float_bits((float)t[s] * cell);
         local_max = std::max(local_max, t[s]);
       }
     }
@@ -255,14 +265,15 @@ extern "C" int wx_tree_upload(WxContext* ctx, const WxTreeDesc* d, WxTree** out)
     return fail(ctx, WX_ERR_INVALID_ARGUMENT, "wx_tree_upload: tab3_elem_bytes must be 1 or 4");
   if (d->n4 >= kChildFlag || d->n3 >= kChildFlag) return fail(ctx, WX_ERR_UNSUPPORTED, "wx_tree_upload: too many nodes");
 
-  std::vector<uint32_t> e5, e4, l3;
+  std::vector<uint32_t> e5, e4;
+  std::vector<uint8_t> l3;
   uint32_t max5 = 0, max4 = 0;
-  int rc = pack_internal(d->n5, 32768, d->kids5, d->vals5, d->tab5, d->n4, e5, &max5);
+  int rc = pack_internal(d->n5, 32768, 128.f, d->kids5, d->vals5, d->tab5, d->n4, e5, &max5);
   if (rc) return fail(ctx, rc, "wx_tree_upload: N5 table (child index out of range or distance >= 2^31)");
-  rc = pack_internal(d->n4, 4096, d->kids4, d->vals4, d->tab4, d->n3, e4, &max4);
+  rc = pack_internal(d->n4, 4096, 8.f, d->kids4, d->vals4, d->tab4, d->n3, e4, &max4);
   if (rc) return fail(ctx, rc, "wx_tree_upload: N4 table (child index out of range or distance >= 2^31)");
 
-  // leaf distance width: the largest inactive-voxel distance decides
+  // leaf distance width: the largest inactive-voxel distance decides (one byte per voxel, else u32)
   const uint8_t* t8 = (const uint8_t*)d->tab3;
   const uint32_t* t32 = (const uint32_t*)d->tab3;
   const bool narrow = d->tab3_elem_bytes == 1;
@@ -277,17 +288,17 @@ extern "C" int wx_tree_upload(WxContext* ctx, const WxTreeDesc* d, WxTree** out)
     }
   });
   const uint32_t max3v = mx3.load();
-  const uint32_t leaf_bits = max3v <= 15 ? 4 : (max3v <= 255 ? 8 : 32);
-  const size_t words_per_leaf = leaf_bits == 4 ? 64 : (leaf_bits == 8 ? 128 : 512);
-  l3.assign((size_t)d->n3 * words_per_leaf, 0u);
+  const uint32_t leaf_bits = max3v <= 255 ? 8 : 32;
+  const uint32_t leaf_shift = leaf_bits == 8 ? 9 : 11;
+  l3.assign((size_t)d->n3 << leaf_shift, 0u);
   parallel_for(d->n3, [&](size_t leaf) {
     const uint64_t* v = d->vals3 + leaf * 8;
-    uint32_t* o = l3.data() + leaf * words_per_leaf;
+    uint8_t* o8 = l3.data() + (leaf << leaf_shift);
+    uint32_t* o32 = reinterpret_cast<uint32_t*>(o8);
     for (uint32_t s = 0; s < 512; ++s) {
       const uint32_t dist = bit(v, s) ? 0u : (narrow ? (uint32_t)t8[leaf * 512 + s] : t32[leaf * 512 + s]);
-      if (leaf_bits == 4) o[s >> 3] |= dist << ((s & 7) * 4);
-      else if (leaf_bits == 8) o[s >> 2] |= dist << ((s & 3) * 8);
-      else o[s] = dist;
+      if (leaf_bits == 8) o8[s] = (uint8_t)dist;
+      else o32[s] = dist;
     }
   });
 
@@ -295,12 +306,17 @@ extern "C" int wx_tree_upload(WxContext* ctx, const WxTreeDesc* d, WxTree** out)
   if (!t) return fail(ctx, WX_ERR_OUT_OF_MEMORY, "wx_tree_upload: host allocation");
   t->ctx = ctx;
   t->origins.resize(d->n5);
-  for (uint32_t i = 0; i < d->n5; ++i) t->origins[i] = make_int4(d->origins[3 * i], d->origins[3 * i + 1], d->origins[3 * i + 2], 0);
+  for (uint32_t i = 0; i < d->n5; ++i)  // biased like the voxel coordinates the kernel derives from float bits (modular)
+    t->origins[i] = make_int4((int)((uint32_t)d->origins[3 * i] + kBias), (int)((uint32_t)d->origins[3 * i + 1] + kBias),
+                              (int)((uint32_t)d->origins[3 * i + 2] + kBias), 0);
+  t->leaf_shift = leaf_shift;
+  // the fast march needs byte leaves and every step size below 2^20 (wx_device.cuh); anything else takes the exact march
+  t->fast_ok = leaf_bits == 8 && (double)max5 * 128.0 < (double)kFastMaxSize && (double)max4 * 8.0 < (double)kFastMaxSize && (double)max3v < (double)kFastMaxSize;
   t->info.n5 = d->n5, t->info.n4 = d->n4, t->info.n3 = d->n3;
   t->info.leaf_bits = leaf_bits;
   t->info.max_dist[0] = max5, t->info.max_dist[1] = max4, t->info.max_dist[2] = max3v;
   t->info.n_devices = (uint32_t)ctx->dev.size();
-  t->info.device_bytes = (e5.size() + e4.size() + l3.size()) * 4 + t->origins.size() * sizeof(int4);
+  t->info.device_bytes = (e5.size() + e4.size()) * 4 + l3.size() + t->origins.size() * sizeof(int4);
   t->on.resize(ctx->dev.size());
 
   auto up = [&](int dev_i) -> int {
@@ -310,11 +326,11 @@ extern "C" int wx_tree_upload(WxContext* ctx, const WxTreeDesc* d, WxTree** out)
     // +256 B of slack keeps zero-sized levels allocatable
     WX_CUDA(ctx, cudaMalloc(&o.e5, e5.size() * 4 + 256));
     WX_CUDA(ctx, cudaMalloc(&o.e4, e4.size() * 4 + 256));
-    WX_CUDA(ctx, cudaMalloc(&o.l3, l3.size() * 4 + 256));
+    WX_CUDA(ctx, cudaMalloc(&o.l3, l3.size() + 256));
     WX_CUDA(ctx, cudaMalloc(&o.origins, t->origins.size() * sizeof(int4) + 256));
     if (!e5.empty()) WX_CUDA(ctx, cudaMemcpyAsync(o.e5, e5.data(), e5.size() * 4, cudaMemcpyHostToDevice, s.stream));
     if (!e4.empty()) WX_CUDA(ctx, cudaMemcpyAsync(o.e4, e4.data(), e4.size() * 4, cudaMemcpyHostToDevice, s.stream));
-    if (!l3.empty()) WX_CUDA(ctx, cudaMemcpyAsync(o.l3, l3.data(), l3.size() * 4, cudaMemcpyHostToDevice, s.stream));
+    if (!l3.empty()) WX_CUDA(ctx, cudaMemcpyAsync(o.l3, l3.data(), l3.size(), cudaMemcpyHostToDevice, s.stream));
     if (!t->origins.empty())
       WX_CUDA(ctx, cudaMemcpyAsync(o.origins, t->origins.data(), t->origins.size() * sizeof(int4), cudaMemcpyHostToDevice, s.stream));
     return WX_OK;
@@ -371,8 +387,12 @@ static int launch_on(WxContext* ctx, int dev_i, const WxTree* tree, const WxStat
   RenderParams P;
   memset(&P, 0, sizeof(P));
   P.tree.e5 = o.e5, P.tree.e4 = o.e4, P.tree.l3 = o.l3, P.tree.origins_g = o.origins;
+  // a child entry keeps its flag bit: node = adj + entry * node_bytes, adj = base - 2^31 * node_bytes
+  P.tree.e4_adj = reinterpret_cast<const char*>(o.e4) - ((uint64_t)kChildFlag << 14);
+  P.tree.l3_adj = reinterpret_cast<const char*>(o.l3) - ((uint64_t)kChildFlag << tree->leaf_shift);
   P.tree.n5 = tree->info.n5, P.tree.n4 = tree->info.n4, P.tree.n3 = tree->info.n3;
-  P.tree.leaf_bits = tree->info.leaf_bits;
+  P.tree.leaf_shift = tree->leaf_shift;
+  P.tree.fast_ok = tree->fast_ok ? 1u : 0u;
   for (uint32_t i = 0; i < kInlineOrigins && i < tree->info.n5; ++i) P.tree.origins_c[i] = tree->origins[i];
   P.n_states = n_states;
   P.width = width, P.height = height;

@@ -2,14 +2,21 @@
 //
 // What this replaces: the body of src/shaders/raycast.comp.wgsl of the reference (cp_main :60-68,
 // hdda_ray :84-126, ray_trace :152-265, reflect_ray2/1 :267-342, get_vdb_leaf_* :360-494).  It is
-// not a translation of that file: the reference reads 2 mask words + 1 atlas texel per tree level
-// (three 3-D textures + five mask buffers); here every level is ONE table of 32-bit entries (or a
-// 4/8-bit brick at the leaf) so a lookup is one load per level, and the bottom-up parent-origin
-// cache (:360-396) is three XORs against the previously visited voxel.
+// not a translation of that file:
+//   * the reference reads 2 mask words + 1 atlas texel per tree level (three 3-D textures + five
+//     mask buffers); here every internal level is ONE table of 32-bit entries and a leaf is one
+//     512-byte brick, so a lookup is one load per level;
+//   * the bottom-up parent-origin cache (:360-396) is three XORs against the voxel visited last;
+//   * voxel coordinates are never converted: floor(p) is one round-down add of 1.5*2^23 whose
+//     float bit pattern IS the (biased) integer coordinate;
+//   * modulo_vec3f (:78-80; three IEEE divisions + three floors per step) is replaced by an exact
+//     floor((x+1/2)/size) built from one MUFU.RCP and fused multiply-adds (proof below), packed two
+//     lanes per instruction with the Blackwell f32x2 forms (FADD2 / FFMA2).
 //
-// Arithmetic contract: IEEE binary32, one rounding per source operation, in the operation order of
-// the WGSL (this translation unit is compiled with -fmad=false; division and sqrt are the IEEE
-// ones).  Results are bit-identical to the CPU oracle, which is how parity is proven.
+// Arithmetic contract: IEEE binary32, one rounding per source operation of the WGSL, in its
+// operation order (this translation unit is compiled with -fmad=false; fused operations appear
+// only where they are provably equal to the separately rounded sequence).  Results are
+// bit-identical to the CPU oracle, which is how parity is proven (tests/test_parity_gpu.py).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -19,29 +26,41 @@
 namespace wx {
 
 // ---------------------------------------------------------------------------------------------
-// Device tree.  All arrays are 256-B aligned (cudaMalloc); node records are 128 KB / 16 KB /
-// 256 B (4-bit leaves) so every node starts on a 128-B line.
+// Device tree.  All arrays are 256-B aligned (cudaMalloc); node records are 128 KB / 16 KB / 512 B
+// (2 KB for wide leaves), so every node starts on a 128-B line.
 //
-//   e5[n5][32768], e4[n4][4096] : u32 entry per slot
+//   e5[n5][32768], e4[n4][4096] : u32 entry per slot, offset order of the reference
 //        bit 31 set  -> child; low 31 bits = child node index (reference DFS index)
-//        bit 31 clear-> tile;  value = SDF distance in cells of the level, 0 = active tile (hit)
-//        (value-mask is tested before child-mask in the reference, raycast.comp.wgsl:431-437; the
-//         packer applies that priority once, at upload)
-//   l3[n3] : one brick per leaf, LEAF_BITS per voxel in offset order (x<<6 | y<<3 | z),
-//        0 = active voxel (hit), else SDF distance in voxels.  LEAF_BITS = 4 when every distance
-//        is <= 15 (always true for leaves that contain an active voxel), else 8, else 32.
+//        bit 31 clear-> tile; the entry is the f32 bit pattern of `size` = SDF distance * cell edge
+//                       (128 for an N5 slot, 8 for an N4 slot), i.e. exactly the value hdda_ray
+//                       computes at raycast.comp.wgsl:104; 0.0f = active tile (hit).
+//        (value-mask is tested before child-mask in the reference, :431-437; the packer applies
+//         that priority once, at upload)
+//   l3[n3] : one brick per leaf, one byte per voxel in offset order (x<<6 | y<<3 | z): 0 = active
+//        voxel (hit), else SDF distance in voxels.  When a distance exceeds 255 the whole level is
+//        stored as u32 per voxel instead (leaf_shift 11 instead of 9).
+//   origins: (x, y, z) + kBias per N5, in the reference's sorted order.
 // ---------------------------------------------------------------------------------------------
+constexpr uint32_t kBias = 0x4B400000u;      // bit pattern of 1.5*2^23: float(kMagic + x) has bits kBias + x
+constexpr float kMagic = 12582912.0f;        // 1.5 * 2^23
+constexpr uint32_t kChildFlag = 0x80000000u;
+constexpr uint32_t kNoCache = 0x80000000u;   // cursor.dbits: nothing cached, every lookup starts at the root
+constexpr uint32_t kInlineOrigins = 8;
+constexpr float kFastMaxSize = 1048576.0f;   // 2^20: largest step size the fast march accepts
+
 struct DevTree {
   const uint32_t* __restrict__ e5;
   const uint32_t* __restrict__ e4;
-  const uint32_t* __restrict__ l3;
-  const int4* __restrict__ origins_g;  // n5 entries (x,y,z,0); used when n5 > kInlineOrigins
+  const uint8_t* __restrict__ l3;
+  // child entry e (flag included) -> node address: adj + e * node_bytes  (adj = base - 2^31 * node_bytes)
+  const char* __restrict__ e4_adj;
+  const char* __restrict__ l3_adj;
+  const int4* __restrict__ origins_g;  // all n5 biased origins; read when n5 > kInlineOrigins
   uint32_t n5, n4, n3;
-  uint32_t leaf_bits;
-  int4 origins_c[8];  // first 8 origins, read from the constant bank
+  uint32_t leaf_shift;                 // log2(bytes per leaf): 9 (u8 voxels) or 11 (u32 voxels)
+  uint32_t fast_ok;                    // every tile/leaf size < kFastMaxSize
+  int4 origins_c[kInlineOrigins];      // first 8 biased origins, read from the constant bank
 };
-constexpr uint32_t kInlineOrigins = 8;
-constexpr uint32_t kChildFlag = 0x80000000u;
 
 struct AovPtrs {
   uint8_t* state;
@@ -97,83 +116,135 @@ __device__ __forceinline__ V3 sign11(V3 d) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Tree cursor: the path to the voxel visited last.  depth = level of the last result
-// (the reference's VdbLeaf.num_parents): 0 nothing cached, 1 n5, 2 n5+n4, 3 n5+n4+n3.
+// Packed binary32 pairs (Blackwell f32x2: one issue slot, two IEEE results).  ptxas turns a pair
+// built from one scalar into a broadcast operand, so bc() costs nothing.
+// NOTE: ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even under --fmad=false (and folds
+// fma2(a, b, -0.0) back into it); where a product must be rounded on its own and then added, the
+// add is done with scalar FADDs, which ptxas leaves alone.
 // ---------------------------------------------------------------------------------------------
-struct Cursor {
-  int lx, ly, lz;
-  uint32_t n5, n4, n3;
-  uint32_t depth;
-};
-
-struct Lookup {
-  uint32_t dist;   // 0 => hit
-  float cell;      // edge of one cell of the level the lookup ended on: 4096, 128, 8, 1
-};
-
-__device__ __forceinline__ uint32_t leaf_dist(const DevTree& T, uint32_t n3, int x, int y, int z) {
-  const uint32_t o3 = ((uint32_t)(x & 7) << 6) | ((uint32_t)(y & 7) << 3) | (uint32_t)(z & 7);
-  if (T.leaf_bits == 4) {
-    const uint32_t w = __ldg(T.l3 + (size_t)n3 * 64 + (o3 >> 3));
-    return (w >> ((o3 & 7) * 4)) & 15u;
-  } else if (T.leaf_bits == 8) {
-    const uint32_t w = __ldg(T.l3 + (size_t)n3 * 128 + (o3 >> 2));
-    return (w >> ((o3 & 3) * 8)) & 255u;
-  }
-  return __ldg(T.l3 + (size_t)n3 * 512 + o3);
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ f32x2 bc(float v) { return pk(v, v); }
+__device__ __forceinline__ float lo(f32x2 v) { return __uint_as_float((uint32_t)v); }
+__device__ __forceinline__ float hi(f32x2 v) { return __uint_as_float((uint32_t)(v >> 32)); }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ f32x2 add2_rd(f32x2 a, f32x2 b) {  // round toward -inf
+  f32x2 d;
+  asm("add.rm.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {  // never feed this to add2/sub2 (see NOTE)
+  f32x2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ float rcp_approx(float v) {  // MUFU.RCP, <= 1 ulp
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+  return r;
 }
 
-// L(pos): pure function of pos; the cursor only shortens the walk.
-__device__ __forceinline__ Lookup lookup(const DevTree& T, Cursor& c, int x, int y, int z) {
-  const uint32_t diff = (uint32_t)((x ^ c.lx) | (y ^ c.ly) | (z ^ c.lz));
-  c.lx = x, c.ly = y, c.lz = z;
+// ---------------------------------------------------------------------------------------------
+// Tree cursor: the path to the voxel visited last.
+//   dbits = 0            : q5, q4, q3 valid (last lookup ended in a leaf,       num_parents 3)
+//           8            : q5, q4 valid     (last lookup ended on an N4 slot,   num_parents 2)
+//           128          : q5 valid         (last lookup ended on an N5 slot,   num_parents 1)
+//           kNoCache|L<<28: nothing reusable (no N5 here, or an N5 that reaches beyond the +-4096 world,
+//                          where the march must test the bounds every step); L = num_parents
+// OR-ing dbits into the coordinate difference makes "same node AND cached that deep" one compare.
+// ---------------------------------------------------------------------------------------------
+struct Cursor {
+  uint32_t lx, ly, lz;  // biased voxel coordinates of the last lookup
+  uint32_t dbits;
+  const uint32_t* q5;
+  const uint32_t* q4;
+  const uint8_t* q3;
+};
+
+__device__ __forceinline__ uint32_t cursor_level(uint32_t dbits) {
+  if (dbits & kNoCache) return (dbits >> 28) & 7u;
+  return dbits == 0u ? 3u : (dbits == 8u ? 2u : 1u);
+}
+
+__device__ __forceinline__ float u32_to_float(uint32_t v) {  // I2FP (alu pipe); a u8/u16 source would go to the XU pipe
+  float f;
+  asm("cvt.rn.f32.u32 %0, %1;" : "=f"(f) : "r"(v));
+  return f;
+}
+
+// Walk down from the level the cursor is still valid for: dv >= 128 starts at the N5 table c.q5,
+// dv >= 8 at the N4 table c.q4, else at the leaf brick c.q3.  Each level's code exists once and the
+// lanes of a warp fall through it together, whatever level they started on.  Returns `size`
+// (0 = hit) and leaves the cursor on the node the walk ended in.
+// WIDE: the leaf level may be stored as u32 per voxel (only the exact march handles that).
+template <bool WIDE>
+__device__ __forceinline__ float descend(const DevTree& T, Cursor& c, uint32_t dv, uint32_t x, uint32_t y, uint32_t z) {
   uint32_t e;
-  if (c.depth == 3 && diff < 8u) goto leaf;
-  if (c.depth >= 2 && diff < 128u) goto node4;
-  if (c.depth >= 1 && diff < 4096u) goto node5;
-  {  // root: first origin equal to (pos >> 12) << 12   (raycast.comp.wgsl:398-413)
-    const int gx = (x >> 12) << 12, gy = (y >> 12) << 12, gz = (z >> 12) << 12;
-    uint32_t found = 0xffffffffu;
-    const uint32_t nc = T.n5 < kInlineOrigins ? T.n5 : kInlineOrigins;
+  if (dv < 8u) goto leaf;
+  if (dv < 128u) goto node4;
+  e = __ldg(c.q5 + (((x << 3) & 0x7C00u) | ((y >> 2) & 0x3E0u) | ((z >> 7) & 31u)));
+  if ((int32_t)e >= 0) {
+    c.dbits = 128u;
+    return __uint_as_float(e);
+  }
+  c.q4 = reinterpret_cast<const uint32_t*>(T.e4_adj + (uint64_t)e * 16384ull);
+node4:
+  e = __ldg(c.q4 + (((x << 5) & 0xF00u) | ((y << 1) & 0xF0u) | ((z >> 3) & 15u)));
+  if ((int32_t)e >= 0) {
+    c.dbits = 8u;
+    return __uint_as_float(e);
+  }
+  c.q3 = reinterpret_cast<const uint8_t*>(T.l3_adj + (WIDE ? ((uint64_t)e << T.leaf_shift) : (uint64_t)e * 512ull));
+leaf:
+  c.dbits = 0u;
+  const uint32_t o3 = ((x & 7u) << 6) | ((y & 7u) << 3) | (z & 7u);
+  if (!WIDE || T.leaf_shift == 9u) return u32_to_float(__ldg(c.q3 + o3));
+  return u32_to_float(__ldg(reinterpret_cast<const uint32_t*>(c.q3) + o3));
+}
+
+// Root: first origin equal to (pos >> 12) << 12 (raycast.comp.wgsl:398-413).  Returns the N5 index or -1.
+static __device__ __noinline__ int find_root(const DevTree& T, uint32_t x, uint32_t y, uint32_t z) {
+  const int gx = (int)(x & ~4095u), gy = (int)(y & ~4095u), gz = (int)(z & ~4095u);
+  int found = -1;
+  const uint32_t nc = T.n5 < kInlineOrigins ? T.n5 : kInlineOrigins;
 #pragma unroll
-    for (uint32_t i = 0; i < kInlineOrigins; ++i) {
-      const int4 o = T.origins_c[i];
-      if (i < nc && found == 0xffffffffu && o.x == gx && o.y == gy && o.z == gz) found = i;
-    }
-    if (found == 0xffffffffu) {
-      for (uint32_t i = kInlineOrigins; i < T.n5; ++i) {
-        const int4 o = __ldg(T.origins_g + i);
-        if (o.x == gx && o.y == gy && o.z == gz) {
-          found = i;
-          break;
-        }
+  for (uint32_t i = 0; i < kInlineOrigins; ++i) {
+    const int4 o = T.origins_c[i];
+    if (i < nc && found < 0 && o.x == gx && o.y == gy && o.z == gz) found = (int)i;
+  }
+  if (found < 0) {
+    for (uint32_t i = kInlineOrigins; i < T.n5; ++i) {
+      const int4 o = __ldg(T.origins_g + i);
+      if (o.x == gx && o.y == gy && o.z == gz) {
+        found = (int)i;
+        break;
       }
     }
-    if (found == 0xffffffffu) {
-      c.depth = 0;
-      return Lookup{1u, 4096.f};
-    }
-    c.n5 = found;
   }
-node5:
-  e = __ldg(T.e5 + (size_t)c.n5 * 32768u +
-            ((((uint32_t)(x & 4095) >> 7) << 10) | (((uint32_t)(y & 4095) >> 7) << 5) | ((uint32_t)(z & 4095) >> 7)));
-  if (!(e & kChildFlag)) {
-    c.depth = 1;
-    return Lookup{e, 128.f};
-  }
-  c.n4 = e & ~kChildFlag;
-node4:
-  e = __ldg(T.e4 + (size_t)c.n4 * 4096u +
-            ((((uint32_t)(x & 127) >> 3) << 8) | (((uint32_t)(y & 127) >> 3) << 4) | ((uint32_t)(z & 127) >> 3)));
-  if (!(e & kChildFlag)) {
-    c.depth = 2;
-    return Lookup{e, 8.f};
-  }
-  c.n3 = e & ~kChildFlag;
-leaf:
-  c.depth = 3;
-  return Lookup{leaf_dist(T, c.n3, x, y, z), 1.f};
+  return found;
+}
+// The N5 at (pos >> 12) << 12 contains positions outside the +-4096 world (origin component not in [-4096, 0]).
+__device__ __forceinline__ bool reaches_beyond(uint32_t x, uint32_t y, uint32_t z) {
+  const uint32_t span = 4096u;  // biased origin - (kBias - 4096) must be 0 or 4096
+  return ((x & ~4095u) - (kBias - 4096u)) > span || ((y & ~4095u) - (kBias - 4096u)) > span || ((z & ~4095u) - (kBias - 4096u)) > span;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -189,29 +260,76 @@ struct HitOut {
 };
 
 constexpr uint32_t kMaxRaySteps = 1000u;
+#ifdef WX_UNROLL  // experiment knob: unroll factor of the fast march loop
+#define WX_STR2(x) #x
+#define WX_STR(x) WX_STR2(x)
+#define WX_UNROLL_PRAGMA _Pragma(WX_STR(unroll WX_UNROLL))
+#else
+#define WX_UNROLL_PRAGMA
+#endif
 
-__device__ __forceinline__ HitOut hdda_ray(const DevTree& T, V3 src, V3 dir) {
+__device__ __forceinline__ bool out_of_bounds(float x, float y, float z) {
+  return 4096.f < fmaxf(fmaxf(fabsf(x), fabsf(y)), fabsf(z));
+}
+
+// Lookup from the root (nothing cached, or the N5 changed).  `beyond` reports that the bounds test of
+// :100-103 can succeed at this position (it cannot inside an N5 whose origin lies in [-4096, 0]^3).
+template <bool WIDE>
+__device__ __forceinline__ float lookup_root(const DevTree& T, Cursor& c, uint32_t x, uint32_t y, uint32_t z, bool& beyond) {
+  const int n5 = find_root(T, x, y, z);
+  beyond = reaches_beyond(x, y, z);
+  if (n5 < 0) {
+    beyond = true;
+    c.dbits = kNoCache;
+    return 4096.f;  // dist 1 at level 0 (:411)
+  }
+  c.q5 = T.e5 + (size_t)n5 * 32768u;
+  const float size = descend<WIDE>(T, c, 128u, x, y, z);
+  if (beyond) c.dbits = kNoCache | (cursor_level(c.dbits) << 28);
+  return size;
+}
+
+// One lookup L(pos) through the cursor.
+template <bool WIDE>
+__device__ __forceinline__ float lookup(const DevTree& T, Cursor& c, uint32_t x, uint32_t y, uint32_t z) {
+  const uint32_t dv = ((x ^ c.lx) | c.dbits) | (y ^ c.ly) | (z ^ c.lz);
+  c.lx = x, c.ly = y, c.lz = z;
+  if (dv < 4096u) return descend<WIDE>(T, c, dv, x, y, z);
+  bool beyond;
+  return lookup_root<WIDE>(T, c, x, y, z, beyond);
+}
+
+__device__ __forceinline__ void finish(const DevTree& T, const Cursor& c, HitOut& out) {
+  out.level = cursor_level(c.dbits);
+  out.n3 = out.level == 3u ? (uint32_t)((size_t)(c.q3 - T.l3) >> T.leaf_shift) : 0u;
+}
+
+// Exact march: the WGSL's operations one by one (IEEE division, floor).  Used for rays the fast
+// march excludes (a direction component so small that 1/dir overflows) and for trees with a step
+// size >= 2^20.
+static __device__ __noinline__ HitOut march_exact(const DevTree& T, V3 src, V3 dir) {
   V3 p = src;
   const V3 step = sign11(dir);
   const V3 step01 = max3(splat(0.f), step);
   const V3 idir = V3{1.f / dir.x, 1.f / dir.y, 1.f / dir.z};
   const V3 nudge = 4e-4f * step;
   uint32_t mask = 0;
-  Cursor c{0, 0, 0, 0, 0, 0, 0};
+  Cursor c{0u, 0u, 0u, kNoCache, nullptr, nullptr, nullptr};
   HitOut out;
+  out.state = 2u;
   uint32_t i = 0;
   for (; i < kMaxRaySteps; ++i) {
-    const int x = __float2int_rd(p.x), y = __float2int_rd(p.y), z = __float2int_rd(p.z);
-    const Lookup l = lookup(T, c, x, y, z);
-    if (l.dist == 0u) {
+    const uint32_t x = (uint32_t)__float2int_rd(p.x) + kBias, y = (uint32_t)__float2int_rd(p.y) + kBias,
+                   z = (uint32_t)__float2int_rd(p.z) + kBias;
+    const float size = lookup<true>(T, c, x, y, z);
+    if (size == 0.f) {
       out.state = 0u;
       break;
     }
-    if (4096.f < fabsf(p.x) || 4096.f < fabsf(p.y) || 4096.f < fabsf(p.z)) {
+    if (out_of_bounds(p.x, p.y, p.z)) {
       out.state = 1u;
       break;
     }
-    const float size = (float)l.dist * l.cell;
     // modulo_vec3f(p, size) = p - size * floor(p / size)
     const V3 m = V3{p.x - size * floorf(p.x / size), p.y - size * floorf(p.y / size), p.z - size * floorf(p.z / size)};
     const V3 tmax = idir * (size * step01 - m);
@@ -223,13 +341,112 @@ __device__ __forceinline__ HitOut hdda_ray(const DevTree& T, V3 src, V3 dir) {
     mask = (uint32_t)bx | ((uint32_t)by << 1) | ((uint32_t)bz << 2);
     p = p + nudge * V3{bx ? 1.f : 0.f, by ? 1.f : 0.f, bz ? 1.f : 0.f};
   }
-  if (i == kMaxRaySteps) out.state = 2u;
   out.p = p;
   out.mask = mask;
   out.i = i;
-  out.level = c.depth;
-  out.n3 = c.n3;
+  finish(T, c, out);
   return out;
+}
+
+// Fast march.  Preconditions (checked by hdda_ray): every |1/dir| < 1e30 (so no tMax is NaN and
+// none overflows) and every size < 2^20.  Differences from the text of :84-126, each value-exact:
+//
+//  (1) floor(p): t = p (+, round down) 1.5*2^23 has the integer floor(p) in its low mantissa bits for
+//      |p| < 2^22; its bit pattern is kBias + floor(p), which is what the tree is indexed with.
+//  (2) size * floor(p / size): for finite p and integer size >= 1, RN(p/size) can only reach an
+//      integer k from the inside of [k, k+1) -- p is at least one ulp away from the lattice plane
+//      k*size, and one ulp of p is more than half an ulp of k times size -- so
+//      floor(RN(p/size)) == floor(p/size) == floor((x + 1/2)/size) with x = floor(p).  (x + 1/2)/size
+//      is at least 1/(2 size) away from every integer, and fma(x, r, r/2) with r = MUFU.RCP(size)
+//      is within 4097.5 * 2^-21.4 / size < 1/(2 size) of it (|x| <= 4096 when the bounds test has
+//      passed), so its floor is exact.  size * that floor is an integer below 2^24: the FMA that
+//      forms it from the round-down add is exact.  (The one input this changes is a denormal
+//      negative p, where RN(p/size) underflows to -0: not reachable from a camera.)
+//  (3) size * step01 is exactly size or 0, so fma(size, step01, -m) rounds once, like the WGSL.
+//  (4) mask: without NaNs, (tx <= ty && tx <= tz) == (tx == min(tx, ty, tz)).
+//  (5) p += 4e-4 * step * mask adds exactly +-4e-4 or +-0: a predicated add.
+//  (6) the bounds test can only succeed where lookup() says so (see Cursor).
+__device__ __forceinline__ float keep(float v) {  // the value stays in its register (no rematerialisation in the loop)
+  asm volatile("" : "+f"(v));
+  return v;
+}
+
+__device__ __forceinline__ HitOut march_fast(const DevTree& T, V3 src, V3 dir, V3 idir) {
+  f32x2 pxy = pk(src.x, src.y);
+  float pz = src.z;
+  const f32x2 dxy = pk(dir.x, dir.y), ixy = pk(idir.x, idir.y);
+  const f32x2 s01xy = pk(keep(dir.x < 0.f ? 0.f : 1.f), keep(dir.y < 0.f ? 0.f : 1.f));
+  const float s01z = keep(dir.z < 0.f ? 0.f : 1.f);
+  const float ndx = keep(dir.x < 0.f ? -4e-4f : 4e-4f), ndy = keep(dir.y < 0.f ? -4e-4f : 4e-4f),
+              ndz = keep(dir.z < 0.f ? -4e-4f : 4e-4f);
+  Cursor c{0u, 0u, 0u, kNoCache, nullptr, nullptr, nullptr};
+  HitOut out;
+  out.state = 2u;
+  float ltx = 1.f, lty = 1.f, ltz = 1.f, lt = 0.f;  // tMax and its minimum of the last step (the mask is derived on exit)
+  uint32_t i = 0;
+  WX_UNROLL_PRAGMA
+  for (; i < kMaxRaySteps; ++i) {
+    const f32x2 txy = add2_rd(pxy, bc(kMagic));
+    const float tz = __fadd_rd(pz, kMagic);
+    const uint32_t x = (uint32_t)txy, y = (uint32_t)(txy >> 32), z = __float_as_uint(tz);
+    const uint32_t dv = ((x ^ c.lx) | c.dbits) | (y ^ c.ly) | (z ^ c.lz);
+    c.lx = x, c.ly = y, c.lz = z;
+    float size;
+    if (dv < 4096u) {
+      size = descend<false>(T, c, dv, x, y, z);
+      if (size == 0.f) {
+        out.state = 0u;
+        break;
+      }
+    } else {
+      bool beyond;
+      size = lookup_root<false>(T, c, x, y, z, beyond);
+      if (size == 0.f) {
+        out.state = 0u;
+        break;
+      }
+      if (beyond && out_of_bounds(lo(pxy), hi(pxy), pz)) {
+        out.state = 1u;
+        break;
+      }
+    }
+    const float r = rcp_approx(size);
+    const float hr = 0.5f * r;
+    const float nms = -kMagic * size;
+    const f32x2 xfxy = add2(txy, bc(-kMagic));                         // float(floor(p)), exact
+    const float xfz = tz - kMagic;
+    const f32x2 qxy = add2_rd(fma2(xfxy, bc(r), bc(hr)), bc(kMagic));  // kMagic + floor(p / size)
+    const float qz = __fadd_rd(fmaf(xfz, r, hr), kMagic);
+    const f32x2 gxy = fma2(qxy, bc(size), bc(nms));                    // size * floor(p / size), exact
+    const float gz = fmaf(qz, size, nms);
+    const f32x2 nmxy = sub2(gxy, pxy);                                 // -modulo_vec3f(p, size)
+    const float nmz = gz - pz;
+    const f32x2 tmxy = mul2(ixy, fma2(bc(size), s01xy, nmxy));         // tMax
+    const float tmz = idir.z * fmaf(size, s01z, nmz);
+    ltx = lo(tmxy), lty = hi(tmxy), ltz = tmz;
+    lt = fminf(fminf(ltx, lty), ltz);
+    // p += t * dir: the product is rounded on its own (scalar adds: ptxas would fuse a packed pair)
+    const f32x2 axy = mul2(bc(lt), dxy);
+    float px = lo(pxy) + lo(axy), py = hi(pxy) + hi(axy);
+    pz = pz + lt * dir.z;
+    if (ltx == lt) px += ndx;
+    if (lty == lt) py += ndy;
+    if (ltz == lt) pz += ndz;
+    pxy = pk(px, py);
+  }
+  out.p = V3{lo(pxy), hi(pxy), pz};
+  out.mask = (uint32_t)(ltx == lt) | ((uint32_t)(lty == lt) << 1) | ((uint32_t)(ltz == lt) << 2);
+  out.i = i;
+  finish(T, c, out);
+  return out;
+}
+
+__device__ __forceinline__ HitOut hdda_ray(const DevTree& T, V3 src, V3 dir) {
+  const V3 idir = V3{1.f / dir.x, 1.f / dir.y, 1.f / dir.z};
+  const bool fast = T.fast_ok && fmaxf(fmaxf(fabsf(idir.x), fabsf(idir.y)), fabsf(idir.z)) < 1e30f &&
+                    fmaxf(fmaxf(fabsf(src.x), fabsf(src.y)), fabsf(src.z)) < 2097152.f;
+  if (fast) return march_fast(T, src, dir, idir);
+  return march_exact(T, src, dir);
 }
 
 // secondary rays share one out-of-line copy of the march

@@ -8,9 +8,12 @@ namespace wx {
 
 constexpr int kTileW = 16, kTileH = 8;  // CTA footprint in pixels
 constexpr int kThreads = 128;
+#ifndef WX_MIN_BLOCKS
+#define WX_MIN_BLOCKS 1  // experiment knob: minimum resident CTAs per SM (caps registers)
+#endif
 
 template <int MODE, bool AOV>
-__global__ void __launch_bounds__(kThreads) raycast_kernel(const __grid_constant__ RenderParams P) {
+__global__ void __launch_bounds__(kThreads, WX_MIN_BLOCKS) raycast_kernel(const __grid_constant__ RenderParams P) {
   // ---- pixel of this thread ------------------------------------------------------------------
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t tx = blockIdx.x % P.tiles_x;
