@@ -59,6 +59,7 @@ struct WxTree {
   WxContext* ctx = nullptr;
   std::vector<TreeOnDevice> on;  // one per context device
   std::vector<int4> origins;  // biased by kBias (wx_device.cuh)
+  int8_t root_grid[64];       // N5 index per 4096^3 cell of [-8192, 8192)^3, -1 = none (DevTree::root_grid)
   uint32_t leaf_shift = 9;    // log2(bytes per leaf brick)
   bool fast_ok = true;        // every step size < 2^20: the fast march applies
   WxTreeInfo info{};
@@ -309,6 +310,14 @@ extern "C" int wx_tree_upload(WxContext* ctx, const WxTreeDesc* d, WxTree** out)
   for (uint32_t i = 0; i < d->n5; ++i)  // biased like the voxel coordinates the kernel derives from float bits (modular)
     t->origins[i] = make_int4((int)((uint32_t)d->origins[3 * i] + kBias), (int)((uint32_t)d->origins[3 * i + 1] + kBias),
                               (int)((uint32_t)d->origins[3 * i + 2] + kBias), 0);
+  memset(t->root_grid, 0xff, sizeof(t->root_grid));
+  for (uint32_t i = d->n5; i-- > 0;) {  // descending: the first of equal origins wins, as in the reference's scan
+    const int32_t* o = d->origins + 3 * i;
+    const int64_t cx = ((int64_t)o[0] >> 12) + 2, cy = ((int64_t)o[1] >> 12) + 2, cz = ((int64_t)o[2] >> 12) + 2;
+    if ((o[0] & 4095) || (o[1] & 4095) || (o[2] & 4095)) continue;  // an unaligned origin never equals (pos >> 12) << 12
+    if (cx < 0 || cx > 3 || cy < 0 || cy > 3 || cz < 0 || cz > 3) continue;
+    t->root_grid[cx * 16 + cy * 4 + cz] = i < 127 ? (int8_t)i : (int8_t)-2;
+  }
   t->leaf_shift = leaf_shift;
   // the fast march needs byte leaves and every step size below 2^20 (wx_device.cuh); anything else takes the exact march
   t->fast_ok = leaf_bits == 8 && (double)max5 * 128.0 < (double)kFastMaxSize && (double)max4 * 8.0 < (double)kFastMaxSize && (double)max3v < (double)kFastMaxSize;
@@ -393,7 +402,7 @@ static int launch_on(WxContext* ctx, int dev_i, const WxTree* tree, const WxStat
   P.tree.n5 = tree->info.n5, P.tree.n4 = tree->info.n4, P.tree.n3 = tree->info.n3;
   P.tree.leaf_shift = tree->leaf_shift;
   P.tree.fast_ok = tree->fast_ok ? 1u : 0u;
-  for (uint32_t i = 0; i < kInlineOrigins && i < tree->info.n5; ++i) P.tree.origins_c[i] = tree->origins[i];
+  memcpy(P.tree.root_grid, tree->root_grid, sizeof(P.tree.root_grid));
   P.n_states = n_states;
   P.width = width, P.height = height;
   P.rgba = reinterpret_cast<uchar4*>(rgba_dev);

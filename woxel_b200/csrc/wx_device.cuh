@@ -45,7 +45,6 @@ constexpr uint32_t kBias = 0x4B400000u;      // bit pattern of 1.5*2^23: float(k
 constexpr float kMagic = 12582912.0f;        // 1.5 * 2^23
 constexpr uint32_t kChildFlag = 0x80000000u;
 constexpr uint32_t kNoCache = 0x80000000u;   // cursor.dbits: nothing cached, every lookup starts at the root
-constexpr uint32_t kInlineOrigins = 8;
 constexpr float kFastMaxSize = 1048576.0f;   // 2^20: largest step size the fast march accepts
 
 struct DevTree {
@@ -55,11 +54,14 @@ struct DevTree {
   // child entry e (flag included) -> node address: adj + e * node_bytes  (adj = base - 2^31 * node_bytes)
   const char* __restrict__ e4_adj;
   const char* __restrict__ l3_adj;
-  const int4* __restrict__ origins_g;  // all n5 biased origins; read when n5 > kInlineOrigins
+  const int4* __restrict__ origins_g;  // all n5 biased origins (scanned only outside the root grid)
   uint32_t n5, n4, n3;
   uint32_t leaf_shift;                 // log2(bytes per leaf): 9 (u8 voxels) or 11 (u32 voxels)
   uint32_t fast_ok;                    // every tile/leaf size < kFastMaxSize
-  int4 origins_c[kInlineOrigins];      // first 8 biased origins, read from the constant bank
+  // N5 index (or -1) of the 4x4x4 root cells covering [-8192, 8192)^3, cell = ((x>>12)+2)*16 + ((y>>12)+2)*4 + (z>>12)+2:
+  // everything a ray can reach from inside the +-4096 world with one level-0 step.  Beyond it, or where the
+  // cell holds -2 (index does not fit a byte): scan origins.
+  int8_t root_grid[64];
 };
 
 struct AovPtrs {
@@ -221,25 +223,22 @@ leaf:
 }
 
 // Root: first origin equal to (pos >> 12) << 12 (raycast.comp.wgsl:398-413).  Returns the N5 index or -1.
-static __device__ __noinline__ int find_root(const DevTree& T, uint32_t x, uint32_t y, uint32_t z) {
+static __device__ __noinline__ int scan_roots(const DevTree& T, uint32_t x, uint32_t y, uint32_t z) {
   const int gx = (int)(x & ~4095u), gy = (int)(y & ~4095u), gz = (int)(z & ~4095u);
-  int found = -1;
-  const uint32_t nc = T.n5 < kInlineOrigins ? T.n5 : kInlineOrigins;
-#pragma unroll
-  for (uint32_t i = 0; i < kInlineOrigins; ++i) {
-    const int4 o = T.origins_c[i];
-    if (i < nc && found < 0 && o.x == gx && o.y == gy && o.z == gz) found = (int)i;
+  for (uint32_t i = 0; i < T.n5; ++i) {
+    const int4 o = __ldg(T.origins_g + i);
+    if (o.x == gx && o.y == gy && o.z == gz) return (int)i;
   }
-  if (found < 0) {
-    for (uint32_t i = kInlineOrigins; i < T.n5; ++i) {
-      const int4 o = __ldg(T.origins_g + i);
-      if (o.x == gx && o.y == gy && o.z == gz) {
-        found = (int)i;
-        break;
-      }
-    }
+  return -1;
+}
+__device__ __forceinline__ int find_root(const DevTree& T, uint32_t x, uint32_t y, uint32_t z) {
+  const uint32_t c0 = (kBias >> 12) - 2u;
+  const uint32_t cx = (x >> 12) - c0, cy = (y >> 12) - c0, cz = (z >> 12) - c0;
+  if ((cx | cy | cz) < 4u) {
+    const int v = (int)T.root_grid[cx * 16u + cy * 4u + cz];
+    if (v != -2) return v;
   }
-  return found;
+  return scan_roots(T, x, y, z);
 }
 // The N5 at (pos >> 12) << 12 contains positions outside the +-4096 world (origin component not in [-4096, 0]).
 __device__ __forceinline__ bool reaches_beyond(uint32_t x, uint32_t y, uint32_t z) {
@@ -260,7 +259,10 @@ struct HitOut {
 };
 
 constexpr uint32_t kMaxRaySteps = 1000u;
-#ifdef WX_UNROLL  // experiment knob: unroll factor of the fast march loop
+#ifndef WX_UNROLL
+#define WX_UNROLL 2  // two steps per loop trip: the cursor's last-voxel registers alternate instead of being copied
+#endif
+#if WX_UNROLL > 1
 #define WX_STR2(x) #x
 #define WX_STR(x) WX_STR2(x)
 #define WX_UNROLL_PRAGMA _Pragma(WX_STR(unroll WX_UNROLL))
@@ -272,31 +274,29 @@ __device__ __forceinline__ bool out_of_bounds(float x, float y, float z) {
   return 4096.f < fmaxf(fmaxf(fabsf(x), fabsf(y)), fabsf(z));
 }
 
-// Lookup from the root (nothing cached, or the N5 changed).  `beyond` reports that the bounds test of
-// :100-103 can succeed at this position (it cannot inside an N5 whose origin lies in [-4096, 0]^3).
-template <bool WIDE>
-__device__ __forceinline__ float lookup_root(const DevTree& T, Cursor& c, uint32_t x, uint32_t y, uint32_t z, bool& beyond) {
+// The N5 changed (or nothing is cached): find the root entry.  On success c.q5 is set and dv becomes 128
+// (walk down from the N5 table); without an N5 dv stays >= 4096 and the cursor caches nothing.  Returns
+// `beyond`: the bounds test of :100-103 can succeed at this position (it cannot inside an N5 whose
+// origin lies in [-4096, 0]^3).
+__device__ __forceinline__ bool enter_root(const DevTree& T, Cursor& c, uint32_t& dv, uint32_t x, uint32_t y, uint32_t z) {
   const int n5 = find_root(T, x, y, z);
-  beyond = reaches_beyond(x, y, z);
   if (n5 < 0) {
-    beyond = true;
     c.dbits = kNoCache;
-    return 4096.f;  // dist 1 at level 0 (:411)
+    return true;
   }
   c.q5 = T.e5 + (size_t)n5 * 32768u;
-  const float size = descend<WIDE>(T, c, 128u, x, y, z);
-  if (beyond) c.dbits = kNoCache | (cursor_level(c.dbits) << 28);
-  return size;
+  dv = 128u;
+  return reaches_beyond(x, y, z);
 }
 
-// One lookup L(pos) through the cursor.
+// One lookup L(pos) through the cursor, for the exact march (bounds tested every step).
 template <bool WIDE>
 __device__ __forceinline__ float lookup(const DevTree& T, Cursor& c, uint32_t x, uint32_t y, uint32_t z) {
-  const uint32_t dv = ((x ^ c.lx) | c.dbits) | (y ^ c.ly) | (z ^ c.lz);
+  uint32_t dv = ((x ^ c.lx) | c.dbits) | (y ^ c.ly) | (z ^ c.lz);
   c.lx = x, c.ly = y, c.lz = z;
-  if (dv < 4096u) return descend<WIDE>(T, c, dv, x, y, z);
-  bool beyond;
-  return lookup_root<WIDE>(T, c, x, y, z, beyond);
+  if (dv >= 4096u) (void)enter_root(T, c, dv, x, y, z);
+  if (dv >= 4096u) return 4096.f;  // no N5 here: dist 1 at level 0 (:411)
+  return descend<WIDE>(T, c, dv, x, y, z);
 }
 
 __device__ __forceinline__ void finish(const DevTree& T, const Cursor& c, HitOut& out) {
@@ -389,26 +389,24 @@ __device__ __forceinline__ HitOut march_fast(const DevTree& T, V3 src, V3 dir, V
     const f32x2 txy = add2_rd(pxy, bc(kMagic));
     const float tz = __fadd_rd(pz, kMagic);
     const uint32_t x = (uint32_t)txy, y = (uint32_t)(txy >> 32), z = __float_as_uint(tz);
-    const uint32_t dv = ((x ^ c.lx) | c.dbits) | (y ^ c.ly) | (z ^ c.lz);
+    uint32_t dv = ((x ^ c.lx) | c.dbits) | (y ^ c.ly) | (z ^ c.lz);
     c.lx = x, c.ly = y, c.lz = z;
+    // lookup L(pos): from the root only when the N5 changed, else from the deepest cached node
     float size;
-    if (dv < 4096u) {
-      size = descend<false>(T, c, dv, x, y, z);
-      if (size == 0.f) {
-        out.state = 0u;
-        break;
-      }
-    } else {
-      bool beyond;
-      size = lookup_root<false>(T, c, x, y, z, beyond);
-      if (size == 0.f) {
-        out.state = 0u;
-        break;
-      }
-      if (beyond && out_of_bounds(lo(pxy), hi(pxy), pz)) {
+    bool beyond = false;
+    if (dv >= 4096u) beyond = enter_root(T, c, dv, x, y, z);
+    if (dv < 4096u) size = descend<false>(T, c, dv, x, y, z);
+    else size = 4096.f;  // no N5 here: dist 1 at level 0 (:411)
+    if (size == 0.f) {
+      out.state = 0u;
+      break;
+    }
+    if (beyond) {  // the only places where the bounds test of :100-103 can succeed (see Cursor)
+      if (out_of_bounds(lo(pxy), hi(pxy), pz)) {
         out.state = 1u;
         break;
       }
+      c.dbits = kNoCache | (cursor_level(c.dbits) << 28);
     }
     const float r = rcp_approx(size);
     const float hr = 0.5f * r;

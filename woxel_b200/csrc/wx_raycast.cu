@@ -9,7 +9,7 @@ namespace wx {
 constexpr int kTileW = 16, kTileH = 8;  // CTA footprint in pixels
 constexpr int kThreads = 128;
 #ifndef WX_MIN_BLOCKS
-#define WX_MIN_BLOCKS 1  // experiment knob: minimum resident CTAs per SM (caps registers)
+#define WX_MIN_BLOCKS 9  // resident CTAs per SM the register budget is capped for (56 registers); measured best of 1/9/10/12
 #endif
 
 template <int MODE, bool AOV>
