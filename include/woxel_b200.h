@@ -169,6 +169,12 @@ int wx_render_device(WxContext *ctx, int device_index, const WxTree *tree, const
 
 int wx_last_render_info(const WxContext *ctx, WxRenderInfo *info);
 
+/* Pure host arithmetic, no device needed: row_mask_out[y] = 1 iff `shard` renders row y of a frame of
+ * `height` rows (the same band dealing wx_render / wx_render_device launch with).  The shards
+ * 0..count-1 partition the rows.  Replaces nothing in the reference (it has one adapter,
+ * src/render/wgpu_context.rs:46-53); it exists so that the multi-GPU split can be tested without GPUs. */
+int wx_shard_rows(uint32_t height, const WxShard *shard, uint8_t *row_mask_out);
+
 /* Device memory helpers so that a host language needs no CUDA runtime binding of its own. */
 int wx_device_alloc(WxContext *ctx, int device_index, size_t bytes, void **out);
 int wx_device_free(WxContext *ctx, int device_index, void *ptr);

@@ -92,6 +92,7 @@ CUDA_API = {
     "wx_ipc_export": (C.c_int, [vp, C.c_int, vp, u8p]),
     "wx_ipc_open": (C.c_int, [vp, C.c_int, u8p, C.POINTER(vp)]),
     "wx_ipc_close": (C.c_int, [vp, C.c_int, vp]),
+    "wx_shard_rows": (C.c_int, [C.c_uint32, C.POINTER(WxShard), vp]),
 }
 f3, u3, i3 = C.POINTER(C.c_float), C.POINTER(C.c_uint32), C.POINTER(C.c_int32)
 HOST_API = {

@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -31,6 +32,10 @@ struct DeviceSlot {
   uint32_t states_cap = 0;
   uint8_t* scratch = nullptr;  // staging frame when peer stores are impossible
   size_t scratch_bytes = 0;
+  cudaStream_t copy_stream = nullptr;   // read-back of finished row chunks while later chunks render
+  cudaStream_t aux[2] = {nullptr, nullptr};  // chunks alternate over stream/aux[0]/aux[1] so that one chunk's drain overlaps the next
+  cudaEvent_t fork = nullptr, join[2] = {nullptr, nullptr};
+  std::vector<cudaEvent_t> chunk_done;  // one per chunk of a pipelined wx_render
 };
 
 struct FrameBuffers {  // device[0]-resident outputs of wx_render
@@ -128,6 +133,12 @@ extern "C" int wx_init(int n_devices, const int* device_ids, WxContext** out) {
     DeviceSlot& s = ctx->dev[i];
     cudaError_t err = cudaSetDevice(s.id);
     if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking);
+    if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&s.copy_stream, cudaStreamNonBlocking);
+    for (int k = 0; k < 2 && err == cudaSuccess; ++k) {
+      err = cudaStreamCreateWithFlags(&s.aux[k], cudaStreamNonBlocking);
+      if (err == cudaSuccess) err = cudaEventCreateWithFlags(&s.join[k], cudaEventDisableTiming);
+    }
+    if (err == cudaSuccess) err = cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming);
     if (err == cudaSuccess) err = cudaEventCreate(&s.ev0);
     if (err == cudaSuccess) err = cudaEventCreate(&s.ev1);
     if (err != cudaSuccess) {
@@ -173,6 +184,13 @@ extern "C" int wx_shutdown(WxContext* ctx) {
     if (s.scratch) (void)cudaFree(s.scratch);
     if (s.ev0) (void)cudaEventDestroy(s.ev0);
     if (s.ev1) (void)cudaEventDestroy(s.ev1);
+    for (cudaEvent_t e : s.chunk_done) (void)cudaEventDestroy(e);
+    if (s.copy_stream) (void)cudaStreamDestroy(s.copy_stream);
+    for (int k = 0; k < 2; ++k) {
+      if (s.aux[k]) (void)cudaStreamDestroy(s.aux[k]);
+      if (s.join[k]) (void)cudaEventDestroy(s.join[k]);
+    }
+    if (s.fork) (void)cudaEventDestroy(s.fork);
     if (s.stream) (void)cudaStreamDestroy(s.stream);
   }
   if (ctx->total0) (void)cudaEventDestroy(ctx->total0);
@@ -388,9 +406,12 @@ extern "C" int wx_tree_info(const WxTree* tree, WxTreeInfo* info) {
 // ---------------------------------------------------------------------------------------------
 // Frame entry points
 // ---------------------------------------------------------------------------------------------
+// Frames [cam0, cam0 + ncam) of `states`, rows [row0, row1) (row1 == 0: all rows; ignored when sharded).
+// `states_on_device`: the whole batch is already in s.d_states (a pipelined wx_render uploads it once).
 static int launch_on(WxContext* ctx, int dev_i, const WxTree* tree, const WxState* states, uint32_t n_states, uint32_t width,
                      uint32_t height, uint8_t* rgba_dev, const WxAov* aov_dev, const WxShard* shard, cudaStream_t stream,
-                     uint32_t* launches_out) {
+                     uint32_t* launches_out, uint32_t cam0 = 0, uint32_t ncam = 0xffffffffu, uint32_t row0 = 0, uint32_t row1 = 0,
+                     bool states_on_device = false) {
   DeviceSlot& s = ctx->dev[dev_i];
   const TreeOnDevice& o = tree->on[dev_i];
   RenderParams P;
@@ -414,24 +435,28 @@ static int launch_on(WxContext* ctx, int dev_i, const WxTree* tree, const WxStat
   if (n_states == 1) {
     P.s0 = states[0];
   } else {
-    if (s.states_cap < n_states) {
-      if (s.d_states) (void)cudaFree(s.d_states);
-      s.d_states = nullptr, s.states_cap = 0;
-      WX_CUDA(ctx, cudaMalloc(&s.d_states, (size_t)n_states * sizeof(WxState)));
-      s.states_cap = n_states;
+    if (!states_on_device) {
+      if (s.states_cap < n_states) {
+        if (s.d_states) (void)cudaFree(s.d_states);
+        s.d_states = nullptr, s.states_cap = 0;
+        WX_CUDA(ctx, cudaMalloc(&s.d_states, (size_t)n_states * sizeof(WxState)));
+        s.states_cap = n_states;
+      }
+      WX_CUDA(ctx, cudaMemcpyAsync(s.d_states, states, (size_t)n_states * sizeof(WxState), cudaMemcpyHostToDevice, stream));
     }
-    WX_CUDA(ctx, cudaMemcpyAsync(s.d_states, states, (size_t)n_states * sizeof(WxState), cudaMemcpyHostToDevice, stream));
     P.states = s.d_states;
   }
+  const uint32_t cam1 = ncam > n_states - cam0 ? n_states : cam0 + ncam;
   uint32_t total_launches = 0;
   // a camera batch is launched per run of equal render modes (normally one run)
-  for (uint32_t b = 0; b < n_states;) {
+  for (uint32_t b = cam0; b < cam1;) {
     uint32_t e = b + 1;
     const uint32_t mode = states[b].render_mode[0] > 4 ? 0 : states[b].render_mode[0];
-    while (e < n_states && (states[e].render_mode[0] > 4 ? 0 : states[e].render_mode[0]) == mode) ++e;
+    while (e < cam1 && (states[e].render_mode[0] > 4 ? 0 : states[e].render_mode[0]) == mode) ++e;
     P.cam_base = b;
     if (shard) P.shard_index = shard->index, P.shard_count = shard->count, P.band_rows = shard->band_rows;
     else P.shard_index = 0, P.shard_count = 1, P.band_rows = 0;
+    P.row_base = row0, P.row_end = row1;
     uint32_t l = 0;
     WX_CUDA(ctx, launch_raycast(P, e - b, mode, stream, &l));
     total_launches += l;
@@ -439,6 +464,11 @@ static int launch_on(WxContext* ctx, int dev_i, const WxTree* tree, const WxStat
   }
   *launches_out = total_launches;
   return WX_OK;
+}
+
+static bool shard_ok(const WxShard* shard) {
+  return !shard || (shard->count != 0 && shard->index < shard->count &&
+                    (shard->count == 1 || (shard->band_rows != 0 && shard->band_rows % kBandRowsMultiple == 0)));
 }
 
 static int check_render_args(WxContext* ctx, const WxTree* tree, const WxState* states, uint32_t n_states, uint32_t width,
@@ -456,8 +486,7 @@ extern "C" int wx_render_device(WxContext* ctx, int device_index, const WxTree* 
   int rc = check_render_args(ctx, tree, states, n_states, width, height, rgba_dev);
   if (rc) return rc;
   if (device_index < 0 || device_index >= (int)ctx->dev.size()) return fail(ctx, WX_ERR_INVALID_ARGUMENT, "render: device index");
-  if (shard && (shard->count == 0 || shard->index >= shard->count ||
-                (shard->count > 1 && (shard->band_rows == 0 || shard->band_rows % kBandRowsMultiple != 0))))
+  if (!shard_ok(shard))
     return fail(ctx, WX_ERR_INVALID_ARGUMENT, "render: bad shard (band_rows must be a positive multiple of 8)");
   DeviceSlot& s = ctx->dev[device_index];
   WX_CUDA(ctx, cudaSetDevice(s.id));
@@ -522,11 +551,74 @@ extern "C" int wx_render(WxContext* ctx, const WxTree* tree, const WxState* stat
   const int ndev = (int)ctx->dev.size();
   WX_CUDA(ctx, cudaEventRecord(ctx->total0, d0.stream));
   uint32_t launches = 0;
+  bool copied = false;  // the frame has already been read back chunk by chunk
   if (ndev == 1) {
     WX_CUDA(ctx, cudaEventRecord(d0.ev0, d0.stream));
-    rc = launch_on(ctx, 0, tree, states, n_states, width, height, ctx->fb.rgba, any_aov ? &dev_aov : nullptr, nullptr, d0.stream, &launches);
-    if (rc) return rc;
-    WX_CUDA(ctx, cudaEventRecord(d0.ev1, d0.stream));
+    // Pipelined read-back: the frame is rendered in chunks (row blocks of one frame, or whole frames of a camera
+    // batch); chunk k travels to the host on the copy stream while chunk k+1 renders.
+    struct Chunk {
+      uint32_t cam0, ncam, row0, row1;
+    };
+    std::vector<Chunk> chunks;
+    if (!any_aov) {
+      if (n_states == 1) {
+        static const uint32_t k_env = getenv("WX_RENDER_CHUNKS") ? (uint32_t)atoi(getenv("WX_RENDER_CHUNKS")) : 0u;  // experiment knob
+        const uint32_t k = k_env ? k_env : ((uint64_t)width * height >= (1u << 20) ? 8u : 1u);
+        const uint32_t rows = ((height + k - 1) / k + kBandRowsMultiple - 1) / kBandRowsMultiple * kBandRowsMultiple;
+        for (uint32_t r = 0; r < height; r += rows) chunks.push_back(Chunk{0, 1, r, std::min(height, r + rows)});
+      } else {
+        const uint32_t per = (n_states + 63) / 64;
+        for (uint32_t c = 0; c < n_states; c += per) chunks.push_back(Chunk{c, std::min(per, n_states - c), 0, height});
+      }
+    }
+    if (chunks.size() <= 1) {
+      rc = launch_on(ctx, 0, tree, states, n_states, width, height, ctx->fb.rgba, any_aov ? &dev_aov : nullptr, nullptr, d0.stream, &launches);
+      if (rc) return rc;
+    } else {
+      while (d0.chunk_done.size() < chunks.size()) {
+        cudaEvent_t e;
+        WX_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        d0.chunk_done.push_back(e);
+      }
+      if (n_states > 1) {  // upload the batch once; the chunk launches read it in place
+        if (d0.states_cap < n_states) {
+          if (d0.d_states) (void)cudaFree(d0.d_states);
+          d0.d_states = nullptr, d0.states_cap = 0;
+          WX_CUDA(ctx, cudaMalloc(&d0.d_states, (size_t)n_states * sizeof(WxState)));
+          d0.states_cap = n_states;
+        }
+        WX_CUDA(ctx, cudaMemcpyAsync(d0.d_states, states, (size_t)n_states * sizeof(WxState), cudaMemcpyHostToDevice, d0.stream));
+      }
+      // A chunk ends with a drain as long as its longest ray; chunks therefore alternate over three streams, so
+      // that the next chunk fills the SMs the previous one is leaving.
+      WX_CUDA(ctx, cudaEventRecord(d0.fork, d0.stream));
+      cudaStream_t ks[3] = {d0.stream, d0.aux[0], d0.aux[1]};
+      for (int k = 0; k < 2; ++k) WX_CUDA(ctx, cudaStreamWaitEvent(d0.aux[k], d0.fork, 0));
+      for (size_t c = 0; c < chunks.size(); ++c) {
+        const Chunk& ch = chunks[c];
+        cudaStream_t st = ks[c % 3];
+        uint32_t l = 0;
+        rc = launch_on(ctx, 0, tree, states, n_states, width, height, ctx->fb.rgba, nullptr, nullptr, st, &l, ch.cam0, ch.ncam,
+                       ch.row0, ch.row1, true);
+        if (rc) return rc;
+        launches += l;
+        WX_CUDA(ctx, cudaEventRecord(d0.chunk_done[c], st));
+        WX_CUDA(ctx, cudaStreamWaitEvent(d0.copy_stream, d0.chunk_done[c], 0));
+        const size_t off = ((size_t)ch.cam0 * height + ch.row0) * width * 4;
+        const size_t bytes = ch.ncam > 1 || ch.row1 - ch.row0 == height ? (size_t)ch.ncam * height * width * 4 : (size_t)(ch.row1 - ch.row0) * width * 4;
+        WX_CUDA(ctx, cudaMemcpyAsync(rgba_out + off, ctx->fb.rgba + off, bytes, cudaMemcpyDeviceToHost, d0.copy_stream));
+      }
+      // join: the main stream waits for the other kernel streams (ev1 = all kernels done), then for the last copy
+      for (int k = 0; k < 2; ++k) {
+        WX_CUDA(ctx, cudaEventRecord(d0.join[k], d0.aux[k]));
+        WX_CUDA(ctx, cudaStreamWaitEvent(d0.stream, d0.join[k], 0));
+      }
+      WX_CUDA(ctx, cudaEventRecord(d0.ev1, d0.stream));
+      WX_CUDA(ctx, cudaEventRecord(d0.fork, d0.copy_stream));
+      WX_CUDA(ctx, cudaStreamWaitEvent(d0.stream, d0.fork, 0));
+      copied = true;
+    }
+    if (!copied) WX_CUDA(ctx, cudaEventRecord(d0.ev1, d0.stream));
     d0.events_pending = true;
   } else {
     // Row bands of one tile height, dealt round-robin: every GPU gets hit-heavy and empty regions.
@@ -572,7 +664,7 @@ extern "C" int wx_render(WxContext* ctx, const WxTree* tree, const WxState* stat
     }
     WX_CUDA(ctx, cudaSetDevice(d0.id));
   }
-  WX_CUDA(ctx, cudaMemcpyAsync(rgba_out, ctx->fb.rgba, npix * 4, cudaMemcpyDeviceToHost, d0.stream));
+  if (!copied) WX_CUDA(ctx, cudaMemcpyAsync(rgba_out, ctx->fb.rgba, npix * 4, cudaMemcpyDeviceToHost, d0.stream));
   for (int k = 0; k < 8; ++k)
     if (host_aov[k]) WX_CUDA(ctx, cudaMemcpyAsync(host_aov[k], ctx->fb.aov[k], npix * aov_elem[k], cudaMemcpyDeviceToHost, d0.stream));
   WX_CUDA(ctx, cudaEventRecord(ctx->total1, d0.stream));
@@ -581,6 +673,21 @@ extern "C" int wx_render(WxContext* ctx, const WxTree* tree, const WxState* stat
   ctx->info = WxRenderInfo{};
   ctx->info.launches = launches;
   ctx->info.rays = (uint64_t)(width / 8 * 8) * (height / 4 * 4) * n_states;
+  return WX_OK;
+}
+
+extern "C" int wx_shard_rows(uint32_t height, const WxShard* shard, uint8_t* row_mask_out) {
+  if (!row_mask_out || !shard_ok(shard)) return fail(nullptr, WX_ERR_INVALID_ARGUMENT, "wx_shard_rows: bad shard (band_rows must be a positive multiple of 8)");
+  memset(row_mask_out, 0, height);
+  if (!shard || shard->count == 1) {
+    memset(row_mask_out, 1, height);
+    return WX_OK;
+  }
+  const uint32_t own = shard_own_bands(height, shard->index, shard->count, shard->band_rows);
+  for (uint32_t k = 0; k < own; ++k) {
+    const uint64_t first = (uint64_t)(k * shard->count + shard->index) * shard->band_rows;
+    for (uint64_t y = first; y < first + shard->band_rows && y < height; ++y) row_mask_out[y] = 1;
+  }
   return WX_OK;
 }
 

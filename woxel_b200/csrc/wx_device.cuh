@@ -87,6 +87,7 @@ struct RenderParams {
   uint32_t own_bands;       // number of row bands this launch renders
   uint32_t tiles_x;         // blocks per row of tiles
   uint32_t tile_rows_per_band;
+  uint32_t row_base, row_end;  // single-shard launches may cover rows [row_base, row_end) only (pipelined read-back)
   uchar4* rgba;
   AovPtrs aov;
   uint32_t has_aov;

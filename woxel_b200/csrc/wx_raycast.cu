@@ -6,10 +6,13 @@
 
 namespace wx {
 
-constexpr int kTileW = 16, kTileH = 8;  // CTA footprint in pixels
-constexpr int kThreads = 128;
+#ifndef WX_CTA_WARPS
+#define WX_CTA_WARPS 4  // 4: CTA = 2x2 warp tiles (16x8 px); 2: 2x1 (16x4 px); 1: one tile (8x4 px)
+#endif
+constexpr int kTileW = WX_CTA_WARPS >= 2 ? 16 : 8, kTileH = WX_CTA_WARPS >= 4 ? 8 : 4;  // CTA footprint in pixels
+constexpr int kThreads = 32 * WX_CTA_WARPS;
 #ifndef WX_MIN_BLOCKS
-#define WX_MIN_BLOCKS 9  // resident CTAs per SM the register budget is capped for (56 registers); measured best of 1/9/10/12
+#define WX_MIN_BLOCKS (36 / WX_CTA_WARPS)  // resident CTAs per SM the register budget is capped for (36 warps -> 56 registers)
 #endif
 
 template <int MODE, bool AOV>
@@ -20,9 +23,9 @@ __global__ void __launch_bounds__(kThreads, WX_MIN_BLOCKS) raycast_kernel(const 
   const uint32_t trow = blockIdx.x / P.tiles_x;                 // tile row among the rows this launch owns
   const uint32_t band = (trow / P.tile_rows_per_band) * P.shard_count + P.shard_index;
   const uint32_t x = tx * kTileW + (warp & 1) * 8 + (lane & 7);
-  const uint32_t y = band * P.band_rows + (trow % P.tile_rows_per_band) * kTileH + (warp >> 1) * 4 + (lane >> 3);
+  const uint32_t y = P.row_base + band * P.band_rows + (trow % P.tile_rows_per_band) * kTileH + (warp >> 1) * 4 + (lane >> 3);
   const uint32_t cam = P.cam_base + blockIdx.y;
-  if (x >= P.width || y >= P.height) return;
+  if (x >= P.width || y >= P.row_end) return;
   const size_t pix = ((size_t)cam * P.height + y) * P.width + x;
   if (x >= P.disp_w || y >= P.disp_h) {  // never dispatched by the reference: zero-initialised texel
     P.rgba[pix] = make_uchar4(0, 0, 0, 0);
@@ -73,13 +76,17 @@ static cudaError_t launch_mode(const RenderParams& P, dim3 grid, cudaStream_t st
 cudaError_t launch_raycast(RenderParams& P, uint32_t n_cams, uint32_t render_mode, cudaStream_t stream, uint32_t* launches) {
   *launches = 0;
   if (P.shard_count == 0) P.shard_count = 1, P.shard_index = 0;
+  if (P.row_end == 0 || P.row_end > P.height) P.row_end = P.height;
   if (P.band_rows == 0 || P.shard_count == 1) {
-    // a single shard owns every row: one band as tall as the frame (rounded up to the tile height)
-    P.band_rows = ((P.height + kTileH - 1) / kTileH) * kTileH;
+    // a single shard owns every row of [row_base, row_end): one band of that height (rounded up to the tile height)
+    if (P.row_base >= P.row_end) return cudaSuccess;
+    P.band_rows = ((P.row_end - P.row_base + kTileH - 1) / kTileH) * kTileH;
     P.shard_count = 1, P.shard_index = 0;
+    P.own_bands = 1;
+  } else {
+    P.row_base = 0, P.row_end = P.height;  // row ranges and band dealing do not combine
+    P.own_bands = shard_own_bands(P.height, P.shard_index, P.shard_count, P.band_rows);
   }
-  const uint32_t total_bands = (P.height + P.band_rows - 1) / P.band_rows;
-  P.own_bands = total_bands > P.shard_index ? (total_bands - P.shard_index + P.shard_count - 1) / P.shard_count : 0;
   P.tiles_x = (P.width + kTileW - 1) / kTileW;
   P.tile_rows_per_band = P.band_rows / kTileH;
   P.disp_w = (P.width / 8) * 8;
