@@ -224,3 +224,53 @@ def test_upload_validation(gpu_ctx):
         ref, ref_aov, _ = g.render(st, 128, 64)
         assert np.array_equal(rgba[0], ref) and np.array_equal(aov["iters"][0], ref_aov["iters"])
         t.free()
+
+
+def _device_count():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+def test_pipelined_readback_equals_single_launch(gpu_ctx):
+    """wx_render without AOVs reads the frame back in chunks while later chunks render (>= 1 Mpx, or a camera
+    batch); the pixels must be those of the single-launch path (the AOV call) and of the oracle."""
+    name, w, h = "icosahedron", 1280, 824  # > 2^20 pixels, height not a multiple of the chunk height
+    tree = gpu_tree(gpu_ctx, name)
+    eye, target = scenes.CAMERAS["oblique_a"]
+    for mode in (0, 3):
+        st = scenes.state_for(eye, target, w, h, mode=mode)
+        plain, _ = gpu_ctx.render(tree, to_wx(st), w, h)           # chunked + pipelined
+        single, _ = gpu_ctx.render(tree, to_wx(st), w, h, aov=True)  # one launch
+        assert gpu_ctx.last_render_info().launches == 1
+        assert np.array_equal(plain, single)
+        ref, _, _ = scenes.get_scene(name).gpu.render(st, w, h, aov=False)
+        assert np.array_equal(plain[0], ref)
+
+
+@pytest.mark.skipif(_device_count() < 2, reason="needs two GPUs")
+def test_multi_device_context_equals_single_device():
+    """One frame / one camera batch split by row bands over every GPU of the box, stored into device 0's frame over
+    NVLink by the kernels themselves: identical to the single-device frame."""
+    n = _device_count()
+    name, w, h = "icosahedron", 640, 360
+    s = scenes.get_scene(name)
+    one = W.Context()
+    many = W.Context(n_devices=n)
+    try:
+        assert many.device_count == n
+        t1, tn = one.upload(s.desc()), many.upload(s.desc())
+        states = [to_wx(scenes.state_for(e, t, w, h, mode=m)) for (e, t), m in
+                  zip([scenes.CAMERAS["default"], scenes.CAMERAS["oblique_a"], scenes.CAMERAS["oblique_b"]], (0, 3, 4))]
+        a, aov_a = one.render(t1, states, w, h, aov=True)
+        b, aov_b = many.render(tn, states, w, h, aov=True)
+        assert np.array_equal(a, b)
+        for k in ("state", "voxel", "leaf", "iters"):
+            assert np.array_equal(aov_a[k], aov_b[k]), k
+        c, _ = many.render(tn, states[1], w, h)
+        assert np.array_equal(c[0], a[1])
+        t1.free(), tn.free()
+    finally:
+        one.close(), many.close()

@@ -22,6 +22,8 @@ using namespace wx;
 // ---------------------------------------------------------------------------------------------
 // Context
 // ---------------------------------------------------------------------------------------------
+constexpr uint32_t kCounterRing = 256;  // launches that may be in flight on one device before a counter is reused
+
 struct DeviceSlot {
   int id = 0;
   cudaStream_t stream = nullptr;
@@ -32,6 +34,9 @@ struct DeviceSlot {
   uint32_t states_cap = 0;
   uint8_t* scratch = nullptr;  // staging frame when peer stores are impossible
   size_t scratch_bytes = 0;
+  uint32_t* counters = nullptr;  // work-queue heads of the persistent kernel, one per launch in flight (ring of kCounterRing)
+  uint32_t counter_next = 0;
+  uint32_t resident_ctas = 0;    // SM count x CTAs per SM
   cudaStream_t copy_stream = nullptr;   // read-back of finished row chunks while later chunks render
   cudaStream_t aux[2] = {nullptr, nullptr};  // chunks alternate over stream/aux[0]/aux[1] so that one chunk's drain overlaps the next
   cudaEvent_t fork = nullptr, join[2] = {nullptr, nullptr};
@@ -134,6 +139,12 @@ extern "C" int wx_init(int n_devices, const int* device_ids, WxContext** out) {
     cudaError_t err = cudaSetDevice(s.id);
     if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking);
     if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&s.copy_stream, cudaStreamNonBlocking);
+    if (err == cudaSuccess) err = cudaMalloc(&s.counters, kCounterRing * sizeof(uint32_t));
+    if (err == cudaSuccess) {
+      int sms = 0;
+      err = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s.id);
+      s.resident_ctas = (uint32_t)sms * kCtasPerSm;
+    }
     for (int k = 0; k < 2 && err == cudaSuccess; ++k) {
       err = cudaStreamCreateWithFlags(&s.aux[k], cudaStreamNonBlocking);
       if (err == cudaSuccess) err = cudaEventCreateWithFlags(&s.join[k], cudaEventDisableTiming);
@@ -182,6 +193,7 @@ extern "C" int wx_shutdown(WxContext* ctx) {
     if (s.stream) (void)cudaStreamSynchronize(s.stream);
     if (s.d_states) (void)cudaFree(s.d_states);
     if (s.scratch) (void)cudaFree(s.scratch);
+    if (s.counters) (void)cudaFree(s.counters);
     if (s.ev0) (void)cudaEventDestroy(s.ev0);
     if (s.ev1) (void)cudaEventDestroy(s.ev1);
     for (cudaEvent_t e : s.chunk_done) (void)cudaEventDestroy(e);
@@ -458,7 +470,8 @@ static int launch_on(WxContext* ctx, int dev_i, const WxTree* tree, const WxStat
     else P.shard_index = 0, P.shard_count = 1, P.band_rows = 0;
     P.row_base = row0, P.row_end = row1;
     uint32_t l = 0;
-    WX_CUDA(ctx, launch_raycast(P, e - b, mode, stream, &l));
+    uint32_t* counter = s.counters + (s.counter_next++ % kCounterRing);
+    WX_CUDA(ctx, launch_raycast(P, e - b, mode, stream, &l, counter, s.resident_ctas));
     total_launches += l;
     b = e;
   }

@@ -88,6 +88,9 @@ struct RenderParams {
   uint32_t tiles_x;         // blocks per row of tiles
   uint32_t tile_rows_per_band;
   uint32_t row_base, row_end;  // single-shard launches may cover rows [row_base, row_end) only (pipelined read-back)
+  // persistent kernel: work queue of 32x16-pixel chunks over the rows this launch owns
+  uint32_t* work_counter;      // zeroed before the launch
+  uint32_t chunks_x, chunks_y, n_chunks;  // per camera: chunks_x * chunks_y; n_chunks = that * cameras of the launch
   uchar4* rgba;
   AovPtrs aov;
   uint32_t has_aov;
@@ -372,21 +375,29 @@ __device__ __forceinline__ float keep(float v) {  // the value stays in its regi
   return v;
 }
 
-__device__ __forceinline__ HitOut march_fast(const DevTree& T, V3 src, V3 dir, V3 idir) {
-  f32x2 pxy = pk(src.x, src.y);
-  float pz = src.z;
-  const f32x2 dxy = pk(dir.x, dir.y), ixy = pk(idir.x, idir.y);
-  const f32x2 s01xy = pk(keep(dir.x < 0.f ? 0.f : 1.f), keep(dir.y < 0.f ? 0.f : 1.f));
-  const float s01z = keep(dir.z < 0.f ? 0.f : 1.f);
-  const float ndx = keep(dir.x < 0.f ? -4e-4f : 4e-4f), ndy = keep(dir.y < 0.f ? -4e-4f : 4e-4f),
-              ndz = keep(dir.z < 0.f ? -4e-4f : 4e-4f);
-  Cursor c{0u, 0u, 0u, kNoCache, nullptr, nullptr, nullptr};
-  HitOut out;
-  out.state = 2u;
-  float ltx = 1.f, lty = 1.f, ltz = 1.f, lt = 0.f;  // tMax and its minimum of the last step (the mask is derived on exit)
-  uint32_t i = 0;
-  WX_UNROLL_PRAGMA
-  for (; i < kMaxRaySteps; ++i) {
+struct FastRay {
+  f32x2 pxy, dxy, ixy, s01xy;
+  float pz, dz, iz, s01z;
+  float ndx, ndy, ndz;
+  float ltx, lty, ltz, lt;  // tMax and its minimum of the last step (the mask is derived on exit)
+  Cursor c;
+  uint32_t i;
+
+  __device__ __forceinline__ void init(V3 src, V3 dir, V3 idir) {
+    pxy = pk(src.x, src.y), pz = src.z;
+    dxy = pk(dir.x, dir.y), dz = dir.z;
+    ixy = pk(idir.x, idir.y), iz = idir.z;
+    s01xy = pk(keep(dir.x < 0.f ? 0.f : 1.f), keep(dir.y < 0.f ? 0.f : 1.f));
+    s01z = keep(dir.z < 0.f ? 0.f : 1.f);
+    ndx = keep(dir.x < 0.f ? -4e-4f : 4e-4f), ndy = keep(dir.y < 0.f ? -4e-4f : 4e-4f), ndz = keep(dir.z < 0.f ? -4e-4f : 4e-4f);
+    ltx = 1.f, lty = 1.f, ltz = 1.f, lt = 0.f;
+    c = Cursor{0u, 0u, 0u, kNoCache, nullptr, nullptr, nullptr};
+    i = 0;
+  }
+
+  // One iteration of hdda_ray's loop body (:90-122) without the counter.  Returns 0 when the ray marched on,
+  // 1 when it hit (state 0), 2 when it left the world (state 1).
+  __device__ __forceinline__ uint32_t step(const DevTree& T) {
     const f32x2 txy = add2_rd(pxy, bc(kMagic));
     const float tz = __fadd_rd(pz, kMagic);
     const uint32_t x = (uint32_t)txy, y = (uint32_t)(txy >> 32), z = __float_as_uint(tz);
@@ -398,15 +409,9 @@ __device__ __forceinline__ HitOut march_fast(const DevTree& T, V3 src, V3 dir, V
     if (dv >= 4096u) beyond = enter_root(T, c, dv, x, y, z);
     if (dv < 4096u) size = descend<false>(T, c, dv, x, y, z);
     else size = 4096.f;  // no N5 here: dist 1 at level 0 (:411)
-    if (size == 0.f) {
-      out.state = 0u;
-      break;
-    }
+    if (size == 0.f) return 1u;
     if (beyond) {  // the only places where the bounds test of :100-103 can succeed (see Cursor)
-      if (out_of_bounds(lo(pxy), hi(pxy), pz)) {
-        out.state = 1u;
-        break;
-      }
+      if (out_of_bounds(lo(pxy), hi(pxy), pz)) return 2u;
       c.dbits = kNoCache | (cursor_level(c.dbits) << 28);
     }
     const float r = rcp_approx(size);
@@ -421,30 +426,55 @@ __device__ __forceinline__ HitOut march_fast(const DevTree& T, V3 src, V3 dir, V
     const f32x2 nmxy = sub2(gxy, pxy);                                 // -modulo_vec3f(p, size)
     const float nmz = gz - pz;
     const f32x2 tmxy = mul2(ixy, fma2(bc(size), s01xy, nmxy));         // tMax
-    const float tmz = idir.z * fmaf(size, s01z, nmz);
+    const float tmz = iz * fmaf(size, s01z, nmz);
     ltx = lo(tmxy), lty = hi(tmxy), ltz = tmz;
     lt = fminf(fminf(ltx, lty), ltz);
     // p += t * dir: the product is rounded on its own (scalar adds: ptxas would fuse a packed pair)
     const f32x2 axy = mul2(bc(lt), dxy);
     float px = lo(pxy) + lo(axy), py = hi(pxy) + hi(axy);
-    pz = pz + lt * dir.z;
+    pz = pz + lt * dz;
     if (ltx == lt) px += ndx;
     if (lty == lt) py += ndy;
     if (ltz == lt) pz += ndz;
     pxy = pk(px, py);
+    return 0u;
   }
-  out.p = V3{lo(pxy), hi(pxy), pz};
-  out.mask = (uint32_t)(ltx == lt) | ((uint32_t)(lty == lt) << 1) | ((uint32_t)(ltz == lt) << 2);
-  out.i = i;
-  finish(T, c, out);
-  return out;
+
+  __device__ __forceinline__ HitOut result(const DevTree& T, uint32_t state) const {
+    HitOut out;
+    out.state = state;
+    out.p = V3{lo(pxy), hi(pxy), pz};
+    out.mask = (uint32_t)(ltx == lt) | ((uint32_t)(lty == lt) << 1) | ((uint32_t)(ltz == lt) << 2);
+    out.i = i;
+    finish(T, c, out);
+    return out;
+  }
+};
+
+__device__ __forceinline__ HitOut march_fast(const DevTree& T, V3 src, V3 dir, V3 idir) {
+  FastRay r;
+  r.init(src, dir, idir);
+  uint32_t state = 2u;
+  WX_UNROLL_PRAGMA
+  for (; r.i < kMaxRaySteps; ++r.i) {
+    const uint32_t s = r.step(T);
+    if (s) {
+      state = s - 1u;
+      break;
+    }
+  }
+  return r.result(T, state);
+}
+
+// The fast march applies to this ray (see its preconditions).
+__device__ __forceinline__ bool fast_ray_ok(const DevTree& T, V3 src, V3 idir) {
+  return T.fast_ok && fmaxf(fmaxf(fabsf(idir.x), fabsf(idir.y)), fabsf(idir.z)) < 1e30f &&
+         fmaxf(fmaxf(fabsf(src.x), fabsf(src.y)), fabsf(src.z)) < 2097152.f;
 }
 
 __device__ __forceinline__ HitOut hdda_ray(const DevTree& T, V3 src, V3 dir) {
   const V3 idir = V3{1.f / dir.x, 1.f / dir.y, 1.f / dir.z};
-  const bool fast = T.fast_ok && fmaxf(fmaxf(fabsf(idir.x), fabsf(idir.y)), fabsf(idir.z)) < 1e30f &&
-                    fmaxf(fmaxf(fabsf(src.x), fabsf(src.y)), fabsf(src.z)) < 2097152.f;
-  if (fast) return march_fast(T, src, dir, idir);
+  if (fast_ray_ok(T, src, idir)) return march_fast(T, src, dir, idir);
   return march_exact(T, src, dir);
 }
 

@@ -1,6 +1,10 @@
 // wx_raycast.cu -- the raycast kernels (cp_main of the reference, src/shaders/raycast.comp.wgsl:60-68)
 // and their launcher.  One thread per primary ray; a warp is an 8x4 pixel tile (the reference's
 // workgroup shape, so that the rays of a warp walk the same nodes); a CTA is 2x2 such tiles.
+#include <algorithm>
+#include <cstdlib>
+#include <string>
+
 #include "wx_device.cuh"
 #include "wx_internal.h"
 
@@ -15,34 +19,18 @@ constexpr int kThreads = 32 * WX_CTA_WARPS;
 #define WX_MIN_BLOCKS (36 / WX_CTA_WARPS)  // resident CTAs per SM the register budget is capped for (36 warps -> 56 registers)
 #endif
 
+struct PixelRef {
+  uint32_t x, y, cam;
+  bool in_frame;    // a pixel of the frame this launch owns
+  bool dispatched;  // inside the reference's dispatch (wgpu_context.rs:281)
+};
+
 template <int MODE, bool AOV>
-__global__ void __launch_bounds__(kThreads, WX_MIN_BLOCKS) raycast_kernel(const __grid_constant__ RenderParams P) {
-  // ---- pixel of this thread ------------------------------------------------------------------
-  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t tx = blockIdx.x % P.tiles_x;
-  const uint32_t trow = blockIdx.x / P.tiles_x;                 // tile row among the rows this launch owns
-  const uint32_t band = (trow / P.tile_rows_per_band) * P.shard_count + P.shard_index;
-  const uint32_t x = tx * kTileW + (warp & 1) * 8 + (lane & 7);
-  const uint32_t y = P.row_base + band * P.band_rows + (trow % P.tile_rows_per_band) * kTileH + (warp >> 1) * 4 + (lane >> 3);
-  const uint32_t cam = P.cam_base + blockIdx.y;
-  if (x >= P.width || y >= P.row_end) return;
-  const size_t pix = ((size_t)cam * P.height + y) * P.width + x;
-  if (x >= P.disp_w || y >= P.disp_h) {  // never dispatched by the reference: zero-initialised texel
-    P.rgba[pix] = make_uchar4(0, 0, 0, 0);
-    return;
-  }
-  const WxState& s = (P.n_states == 1) ? P.s0 : P.states[cam];
-
-  // ---- cp_main -------------------------------------------------------------------------------
-  const float px = (float)x + 0.001f, py = (float)y + 0.001f;
-  const V3 u = V3{s.u[0], s.u[1], s.u[2]}, mv = V3{s.mv[0], s.mv[1], s.mv[2]}, wp = V3{s.wp[0], s.wp[1], s.wp[2]};
-  const V3 eye = V3{s.eye[0], s.eye[1], s.eye[2]};
-  const V3 dir = normalize3((px * u + py * mv) + wp);
-
-  const HitOut hit = hdda_ray(P.tree, eye, dir);
+__device__ __forceinline__ void shade_and_store(const RenderParams& P, const PixelRef& q, const HitOut& hit, V3 dir) {
+  const WxState& s = (P.n_states == 1) ? P.s0 : P.states[q.cam];
+  const size_t pix = ((size_t)q.cam * P.height + q.y) * P.width + q.x;
   const V3 col = shade<MODE>(P.tree, s, hit, dir);
   P.rgba[pix] = make_uchar4((unsigned char)unorm8(col.x), (unsigned char)unorm8(col.y), (unsigned char)unorm8(col.z), 255);
-
   if (AOV) {
     const AovPtrs& a = P.aov;
     if (a.state) a.state[pix] = (uint8_t)hit.state;
@@ -55,12 +43,87 @@ __global__ void __launch_bounds__(kThreads, WX_MIN_BLOCKS) raycast_kernel(const 
     if (a.level) a.level[pix] = (uint8_t)hit.level;
     if (a.iters) a.iters[pix] = hit.i;
     if (a.depth) {
-      const V3 d = hit.p - eye;
+      const V3 d = hit.p - V3{s.eye[0], s.eye[1], s.eye[2]};
       a.depth[pix] = sqrtf(dot3(d, d));
     }
     if (a.mask) a.mask[pix] = (uint8_t)hit.mask;
     if (a.pos) a.pos[3 * pix + 0] = hit.p.x, a.pos[3 * pix + 1] = hit.p.y, a.pos[3 * pix + 2] = hit.p.z;
   }
+}
+
+// cp_main (:60-68) for one pixel: ray generation, hdda_ray, ray_trace, store.
+template <int MODE, bool AOV>
+__device__ __forceinline__ void render_pixel(const RenderParams& P, const PixelRef& q) {
+  if (!q.in_frame) return;
+  if (!q.dispatched) {  // never dispatched by the reference: zero-initialised texel
+    P.rgba[((size_t)q.cam * P.height + q.y) * P.width + q.x] = make_uchar4(0, 0, 0, 0);
+    return;
+  }
+  const WxState& s = (P.n_states == 1) ? P.s0 : P.states[q.cam];
+  const float px = (float)q.x + 0.001f, py = (float)q.y + 0.001f;
+  const V3 u = V3{s.u[0], s.u[1], s.u[2]}, mv = V3{s.mv[0], s.mv[1], s.mv[2]}, wp = V3{s.wp[0], s.wp[1], s.wp[2]};
+  const V3 eye = V3{s.eye[0], s.eye[1], s.eye[2]};
+  const V3 dir = normalize3((px * u + py * mv) + wp);
+  shade_and_store<MODE, AOV>(P, q, hdda_ray(P.tree, eye, dir), dir);
+}
+
+// Tiled kernel: one thread per pixel of the grid, a warp per 8x4 tile, a CTA per 2x2 tiles.
+template <int MODE, bool AOV>
+__global__ void __launch_bounds__(kThreads, WX_MIN_BLOCKS) raycast_kernel(const __grid_constant__ RenderParams P) {
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t tx = blockIdx.x % P.tiles_x;
+  const uint32_t trow = blockIdx.x / P.tiles_x;                 // tile row among the rows this launch owns
+  const uint32_t band = (trow / P.tile_rows_per_band) * P.shard_count + P.shard_index;
+  PixelRef q;
+  q.x = tx * kTileW + (warp & 1) * 8 + (lane & 7);
+  q.y = P.row_base + band * P.band_rows + (trow % P.tile_rows_per_band) * kTileH + (warp >> 1) * 4 + (lane >> 3);
+  q.cam = P.cam_base + blockIdx.y;
+  q.in_frame = q.x < P.width && q.y < P.row_end;
+  q.dispatched = q.x < P.disp_w && q.y < P.disp_h;
+  render_pixel<MODE, AOV>(P, q);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Persistent kernel: the grid is the number of CTAs the device holds at once; every warp pulls 8x4-pixel
+// tiles from a global counter until the frame is done.  Tiles are numbered so that 16 consecutive ones
+// form a 32x16-pixel block: the tiles a warp (and an SM) works on one after the other are neighbours and
+// find their nodes in L1.  Compared with the tiled grid this removes the CTA tail (a CTA slot is held
+// until its longest warp ends: ncu shows 47 % warps active of the 56 % the registers allow).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ PixelRef pixel_of(const RenderParams& P, uint32_t tile, uint32_t lane) {
+  const uint32_t chunk = tile >> 4, t = tile & 15u;
+  const uint32_t per_cam = P.chunks_x * P.chunks_y;
+  const uint32_t cam_i = chunk / per_cam, rem = chunk - cam_i * per_cam;
+  const uint32_t cy = rem / P.chunks_x, cx = rem - cy * P.chunks_x;
+  PixelRef q;
+  q.x = (cx * 4u + (t & 3u)) * 8u + (lane & 7u);
+  const uint32_t vrow = (cy * 4u + (t >> 2)) * 4u + (lane >> 3);  // row among the rows this launch owns
+  const uint32_t band = (vrow / P.band_rows) * P.shard_count + P.shard_index;
+  q.y = P.row_base + band * P.band_rows + vrow % P.band_rows;
+  q.cam = P.cam_base + cam_i;
+  q.in_frame = q.x < P.width && q.y < P.row_end && vrow < P.own_bands * P.band_rows;
+  q.dispatched = q.x < P.disp_w && q.y < P.disp_h;
+  return q;
+}
+
+template <int MODE, bool AOV>
+__global__ void __launch_bounds__(kThreads, WX_MIN_BLOCKS) raycast_persistent(const __grid_constant__ RenderParams P) {
+  const uint32_t lane = threadIdx.x & 31;
+  for (;;) {
+    uint32_t tile = 0;
+    if (lane == 0) tile = atomicAdd(P.work_counter, 1u);
+    tile = __shfl_sync(0xffffffffu, tile, 0);
+    if (tile >= P.n_chunks * 16u) break;
+    render_pixel<MODE, AOV>(P, pixel_of(P, tile, lane));
+    __syncwarp();
+  }
+}
+
+template <int MODE>
+static cudaError_t launch_mode_persistent(const RenderParams& P, unsigned ctas, cudaStream_t stream) {
+  if (P.has_aov) raycast_persistent<MODE, true><<<ctas, kThreads, 0, stream>>>(P);
+  else raycast_persistent<MODE, false><<<ctas, kThreads, 0, stream>>>(P);
+  return cudaGetLastError();
 }
 
 template <int MODE>
@@ -70,10 +133,19 @@ static cudaError_t launch_mode(const RenderParams& P, dim3 grid, cudaStream_t st
   return cudaGetLastError();
 }
 
+// WX_KERNEL=persistent selects the work-queue kernel.  Measured on the 4K sphere frame (profiles/r1_variants_e.txt):
+// tiled 0.995 ms, persistent 1.006 ms -- the CTA tail the queue removes is not what limits the tiled grid, so the
+// simpler kernel is the default.
+static bool use_persistent() {
+  static const bool on = getenv("WX_KERNEL") && std::string(getenv("WX_KERNEL")) == "persistent";
+  return on;
+}
+
 // Fills the launch geometry of P (shard -> bands -> tile rows) and launches frames
 // [P.cam_base, P.cam_base + n_cams) in render mode `render_mode` (the caller groups a camera batch
 // by mode).  P.n_states is the total number of states behind P.states / P.s0.
-cudaError_t launch_raycast(RenderParams& P, uint32_t n_cams, uint32_t render_mode, cudaStream_t stream, uint32_t* launches) {
+cudaError_t launch_raycast(RenderParams& P, uint32_t n_cams, uint32_t render_mode, cudaStream_t stream, uint32_t* launches,
+                           uint32_t* work_counter, uint32_t resident_ctas) {
   *launches = 0;
   if (P.shard_count == 0) P.shard_count = 1, P.shard_index = 0;
   if (P.row_end == 0 || P.row_end > P.height) P.row_end = P.height;
@@ -94,6 +166,28 @@ cudaError_t launch_raycast(RenderParams& P, uint32_t n_cams, uint32_t render_mod
   if (P.own_bands == 0 || n_cams == 0 || P.tiles_x == 0) return cudaSuccess;
   const uint64_t blocks = (uint64_t)P.tiles_x * P.tile_rows_per_band * P.own_bands;
   if (blocks > 0x7fffffffull || n_cams > 65535u) return cudaErrorInvalidConfiguration;
+  if (work_counter && use_persistent()) {
+    const uint64_t own_rows = (uint64_t)P.own_bands * P.band_rows;
+    P.chunks_x = (P.width + 31u) / 32u;
+    P.chunks_y = (uint32_t)((own_rows + 15u) / 16u);
+    const uint64_t n_chunks = (uint64_t)P.chunks_x * P.chunks_y * n_cams;
+    if (n_chunks < (1ull << 27)) {  // the tile counter (16 per chunk) must fit 32 bits
+      P.n_chunks = (uint32_t)n_chunks;
+      P.work_counter = work_counter;
+      cudaError_t e = cudaMemsetAsync(work_counter, 0, sizeof(uint32_t), stream);
+      if (e != cudaSuccess) return e;
+      // one warp per tile at most; otherwise every resident CTA slot of the device
+      const unsigned ctas = (unsigned)std::min<uint64_t>((n_chunks * 16 + WX_CTA_WARPS - 1) / WX_CTA_WARPS, resident_ctas ? resident_ctas : 148u * (unsigned)(WX_MIN_BLOCKS));
+      *launches = 1;
+      switch (render_mode) {
+        case 1: return launch_mode_persistent<1>(P, ctas, stream);
+        case 2: return launch_mode_persistent<2>(P, ctas, stream);
+        case 3: return launch_mode_persistent<3>(P, ctas, stream);
+        case 4: return launch_mode_persistent<4>(P, ctas, stream);
+        default: return launch_mode_persistent<0>(P, ctas, stream);
+      }
+    }
+  }
   dim3 grid((unsigned)blocks, n_cams, 1);
   *launches = 1;
   switch (render_mode) {
