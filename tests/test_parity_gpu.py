@@ -274,3 +274,74 @@ def test_multi_device_context_equals_single_device():
         t1.free(), tn.free()
     finally:
         one.close(), many.close()
+
+
+def _product_scene(kind):
+    """A procedural scene of the benchmark configs built by the PRODUCT host (set_voxel tree -> compute_sdf -> to_flat);
+    the oracle renders from the same tables (its own compute_sdf is compared with the product's in test_host_vs_oracle)."""
+    if kind == "torus":  # BASELINE config 3 at 1/8 scale
+        v = W.VDB345.torus(half=128, major=88.0, minor=31.0, band=2.0)
+    elif kind == "fog":  # BASELINE config 4 at 1/16 scale: dense value-noise fog, high leaf occupancy
+        v = W.VDB345.fog(half=64, tau=0.32)
+        assert 0.05 < v.occupancy < 0.95
+    else:
+        raise KeyError(kind)
+    v.compute_sdf()
+    f = v.to_flat(narrow_leaves=False)
+    g = O.gpudata_from_tables(f.origins, f.kids5, f.vals5, f.tab5, f.kids4, f.vals4, f.tab4, f.vals3, f.tab3)
+    return f, g
+
+
+@pytest.mark.parametrize("kind", ["torus", "fog"])
+def test_procedural_config_scenes(gpu_ctx, kind):
+    f, g = _product_scene(kind)
+    tree = gpu_ctx.upload(f)
+    w, h = 384, 216
+    cams = [((0.5, 0.5, -320.5), (0.5, 0.5, 0.5)), ((210.0, 140.0, -230.0), (0.0, 0.0, 0.0))]
+    if kind == "fog":
+        cams.append(((3.5, 2.5, 1.5), (60.0, 40.0, 50.0)))  # inside the volume: long divergent rays
+    try:
+        for eye, target in cams:
+            for mode in (0, 2, 3, 4):
+                st = scenes.state_for(eye, target, w, h, mode=mode)
+                rgba, aov = gpu_ctx.render(tree, to_wx(st), w, h, aov=True)
+                ref, ref_aov, _ = g.render(st, w, h)
+                assert np.array_equal(rgba[0], ref), (kind, eye, mode)
+                for k in ("state", "voxel", "leaf", "level", "iters", "mask"):
+                    assert np.array_equal(aov[k][0], ref_aov[k]), (kind, eye, mode, k)
+    finally:
+        tree.free()
+
+
+def test_orbit_camera_batch_config5(gpu_ctx):
+    """BASELINE config 5 in small: a 16-camera orbit rendered as one batch == the per-camera frames == the oracle."""
+    import bench
+    name, w, h = "small_sphere", 192, 108
+    tree = gpu_tree(gpu_ctx, name)
+    s = scenes.get_scene(name)
+    sts = []
+    for k in range(16):
+        th = 2 * np.pi * k / 16
+        eye = (0.5 + 150 * np.cos(np.radians(20)) * np.sin(th), 0.5 + 150 * np.sin(np.radians(20)), 0.5 - 150 * np.cos(np.radians(20)) * np.cos(th))
+        sts.append(scenes.state_for(eye, (0.5, 0.5, 0.5), w, h, mode=0))
+    batch, _ = gpu_ctx.render(tree, [to_wx(st) for st in sts], w, h)
+    for k in (0, 5, 11, 15):
+        ref, _, _ = s.gpu.render(sts[k], w, h, aov=False)
+        assert np.array_equal(batch[k], ref), k
+    assert bench.orbit_eye(0) == (0.5, 0.5, -2500.5)
+
+
+def test_persistent_work_queue_kernel_is_bit_identical():
+    """WX_KERNEL=persistent selects the persistent-thread work-queue kernel (read once per process): the same
+    parity tests must pass through it."""
+    import os
+    import subprocess
+    import sys
+    if os.environ.get("WX_KERNEL") == "persistent":
+        pytest.skip("already running under the persistent kernel")
+    env = dict(os.environ, WX_KERNEL="persistent")
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(here, "test_parity_gpu.py"), "-m", "gpu", "-x", "-q", "-k",
+                        "assets_all_modes or edge_cases or camera_batch_and_shards or synthetic_scenes or zero_directions"],
+                       env=env, capture_output=True, text=True, timeout=1200)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
