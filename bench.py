@@ -55,8 +55,9 @@ def orbit_eye(k: int, n: int = 64, radius: float = 2500.0, elevation_deg: float 
     return (0.5 + r * math.cos(el) * math.sin(th), 0.5 + r * math.sin(el), 0.5 - r * math.cos(el) * math.cos(th))
 
 
-def build_scene(name: str):
-    """Returns (VDB345 with SDF, FlatTree u32, description string).  Product host code only."""
+def build_scene(name: str, ctx=None):
+    """Returns (VDB345, FlatTree with SDF, description string, timings).  Product code only: with a device context the
+    SDF sweep runs on the GPU (wx_compute_sdf, same values as the host sweep), else on the host."""
     import woxel_b200 as W
     import scenes
     t0 = time.time()
@@ -76,6 +77,12 @@ def build_scene(name: str):
         # rebuild the asset in the product tree from the golden topology
         v = scenes.host_tree_from_scene(_TopoView(t))
     t1 = time.time()
+    if ctx is not None:
+        flat = v.to_flat(narrow_leaves=False)
+        t2 = time.time()
+        info = flat.compute_sdf_gpu(ctx)
+        return v, flat, what, {"build_s": round(t1 - t0, 2), "flat_s": round(t2 - t1, 2), "sdf_gpu_s": round(time.time() - t2, 3),
+                               "sdf_gpu_device_ms": round(info.device_ms, 2)}
     v.compute_sdf()
     t2 = time.time()
     flat = v.to_flat(narrow_leaves=False)
@@ -235,8 +242,8 @@ def main():
     from woxel_b200 import _ffi
     lib = _ffi.cuda_lib()
 
-    v, flat, what, prep = build_scene(args.scene)
     ctx = W.Context()  # current device
+    v, flat, what, prep = build_scene(args.scene, ctx)
     tree = ctx.upload(flat)
     state = make_state(args.scene, rank)
     frame_bytes = WIDTH * HEIGHT * 4

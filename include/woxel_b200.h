@@ -146,6 +146,27 @@ int wx_tree_upload(WxContext *ctx, const WxTreeDesc *desc, WxTree **out);
 int wx_tree_free(WxContext *ctx, WxTree *tree);
 int wx_tree_info(const WxTree *tree, WxTreeInfo *info);
 
+typedef struct WxSdfInfo {
+  uint32_t max_dist[3]; /* largest distance written to tab5 / tab4 / tab3 */
+  uint32_t reserved;
+  float device_ms;      /* device time of the sweeps (CUDA events), without the host<->device copies */
+  float total_ms;       /* wall time of the call */
+} WxSdfInfo;
+
+/*
+ * VDB345::compute_sdf (src/vdb/vdb345.rs:290-628) on the GPU: the step the reference runs on the CPU
+ * between reading a model and uploading it (src/render/wgpu_context.rs:104, :513).  `topo` carries the
+ * topology exactly as for wx_tree_upload (masks; tab5 / tab4 hold the child index where the child bit
+ * is set, their other entries and tab3 are ignored).  On return tab5_out / tab4_out hold what
+ * vdb.atlas() holds after vdb.compute_sdf(): the child index where the child bit is set, else the
+ * distance; tab3_out holds the distance of every inactive voxel (0 where active), as u8
+ * (tab3_elem_bytes == 1) or u32 (== 4).  The results equal the reference's sequential, order-dependent
+ * sweep value for value.  WX_ERR_UNSUPPORTED: a leaf distance does not fit (retry with
+ * tab3_elem_bytes = 4; distances >= 32768 are not supported on this path).  Out arrays are host memory.
+ */
+int wx_compute_sdf(WxContext *ctx, const WxTreeDesc *topo, uint32_t *tab5_out, uint32_t *tab4_out, void *tab3_out,
+                   uint32_t tab3_elem_bytes, WxSdfInfo *info);
+
 /*
  * One frame per state (n_states > 1 = camera batch).  Blocking.  rgba_out is HOST memory,
  * n_states x height x width x 4 bytes (pinned memory makes the read-back faster; pageable works).
@@ -168,6 +189,17 @@ int wx_render_device(WxContext *ctx, int device_index, const WxTree *tree, const
                      void *stream);
 
 int wx_last_render_info(const WxContext *ctx, WxRenderInfo *info);
+
+/*
+ * Capture step after the raycast (replaces the copy_texture_to_buffer + recorder conversion of
+ * src/render/wgpu_context.rs:374-405 and src/render/recorder.rs:20-37, :132-140): converts the frame(s)
+ * the last wx_render left on device 0 from RGBA8 to RGB8, every colour byte passed through the
+ * reference's linear_to_srgb, and copies them to rgb_out (host, n_states x height x width x 3 bytes).
+ * The arguments must be those of that wx_render call.
+ */
+int wx_capture_srgb(WxContext *ctx, uint32_t n_states, uint32_t width, uint32_t height, uint8_t *rgb_out);
+/* The 256-entry transfer table wx_capture_srgb applies (host arithmetic, no device needed). */
+int wx_srgb_table(uint8_t table_out[256]);
 
 /* Pure host arithmetic, no device needed: row_mask_out[y] = 1 iff `shard` renders row y of a frame of
  * `height` rows (the same band dealing wx_render / wx_render_device launch with).  The shards

@@ -81,6 +81,11 @@ int wxh_renderer_set_options(WxhRenderer *r, uint32_t render_mode, const uint32_
 /* Scene.camera in, rgba8 frame (height x width x 4, host) out */
 int wxh_renderer_render(WxhRenderer *r, const float eye[3], const float target[3], const float up[3], float aspect,
                         float fovy_deg, uint8_t *rgba_out);
+/* compute_sdf of change_vdb_model on the GPU (default 1; wx_compute_sdf, identical values) or on the host (0) */
+int wxh_renderer_set_sdf_on_gpu(WxhRenderer *r, int on);
+void wxh_renderer_last_sdf(const WxhRenderer *r, WxSdfInfo *out); /* device_ms == 0: the host sweep ran */
+/* fills the distances of a flat tree (taken before compute_sdf) on the GPU; WX_ERR_UNSUPPORTED: use wxh_vdb_compute_sdf */
+int wxh_flat_compute_sdf_gpu(WxhFlat *f, WxContext *ctx, WxSdfInfo *info);
 WxContext *wxh_renderer_context(WxhRenderer *r);
 WxTree *wxh_renderer_tree(WxhRenderer *r);
 

@@ -150,6 +150,10 @@ typedef struct WxoStats {
 void wxo_render(const WxoGpuData *g, const WxoState *s, uint32_t width, uint32_t height, uint32_t y0, uint32_t y1,
                 uint8_t *rgba, const WxoAov *aov, int threads, WxoStats *stats);
 
+/* ---- capture (src/render/recorder.rs:20-37, :132-140) ----------------------------------------- */
+uint8_t wxo_linear_to_srgb(uint8_t value);
+void wxo_frame_to_srgb_rgb(const uint8_t* rgba, size_t n_pixels, uint8_t* rgb);
+
 #ifdef __cplusplus
 }
 #endif

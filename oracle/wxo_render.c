@@ -645,3 +645,19 @@ void wxo_default_sun(float dir3[3], float color3[3], float *intensity) {
   color3[0] = 255.f / 255.f, color3[1] = 210.f / 255.f, color3[2] = 160.f / 255.f;
   *intensity = 1.0f;
 }
+
+/* linear_to_srgb (src/render/recorder.rs:132-140): the byte-wise transfer function the recorder applies to
+ * every colour channel of a captured frame before encoding (Frame::ndarray_frame, :20-37, drops alpha). */
+uint8_t wxo_linear_to_srgb(uint8_t value) {
+  const float c = (float)value / 255.0f;
+  float srgb;
+  if (c <= 0.0031308f) srgb = 12.92f * c;
+  else srgb = 1.055f * powf(c, 1.0f / 2.4f) - 0.055f;
+  return (uint8_t)roundf(srgb * 255.0f); /* f32::round: half away from zero; `as u8` saturates, in range here */
+}
+
+/* Frame::ndarray_frame: RGBA8 [n] -> RGB8 [n] through wxo_linear_to_srgb */
+void wxo_frame_to_srgb_rgb(const uint8_t* rgba, size_t n_pixels, uint8_t* rgb) {
+  for (size_t i = 0; i < n_pixels; ++i)
+    for (int k = 0; k < 3; ++k) rgb[3 * i + k] = wxo_linear_to_srgb(rgba[4 * i + k]);
+}

@@ -157,7 +157,9 @@ def test_product_host_path_matches_oracle(gpu_ctx):
     """Reference-facing surface end to end: VDB345 (procedural) -> compute_sdf -> Renderer.render vs oracle."""
     v = W.VDB345.sphere(half=128, radius=100.0, band=2.0)
     r = W.Renderer(320, 200)
-    r.change_vdb_model(v)  # runs the product's compute_sdf + to_flat + wx_tree_upload
+    r.change_vdb_model(v)  # the product's model load: to_flat + wx_compute_sdf (GPU sweep) + wx_tree_upload
+    assert r.last_sdf.device_ms > 0 and list(r.last_sdf.max_dist)[2] > 0
+    v.compute_sdf()  # host sweep: the tables the oracle renders from
     f = v.to_flat(narrow_leaves=False)
     g = O.gpudata_from_tables(f.origins, f.kids5, f.vals5, f.tab5, f.kids4, f.vals4, f.tab4, f.vals3, f.tab3)
     for mode in (W.RenderMode.Diffuse, W.RenderMode.Gray, W.RenderMode.Glossy):
@@ -167,6 +169,9 @@ def test_product_host_path_matches_oracle(gpu_ctx):
         st = scenes.state_for(sc.camera.eye, sc.camera.target, 320, 200, mode=int(mode))
         ref, _, _ = g.render(st, 320, 200, aov=False)
         assert np.array_equal(img, ref), int(mode)
+    r.change_vdb_model(v, compute_sdf=False)  # v now carries the host sweep's distances: same frames
+    assert r.last_sdf.device_ms == 0
+    assert np.array_equal(r.render(sc), img)
 
 
 def test_camera_batch_and_shards_equal_single_frames(gpu_ctx):

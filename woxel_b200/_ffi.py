@@ -54,6 +54,10 @@ class WxTreeInfo(C.Structure):
     ]
 
 
+class WxSdfInfo(C.Structure):
+    _fields_ = [("max_dist", C.c_uint32 * 3), ("reserved", C.c_uint32), ("device_ms", C.c_float), ("total_ms", C.c_float)]
+
+
 class WxRenderInfo(C.Structure):
     _fields_ = [("kernel_ms", C.c_float), ("total_ms", C.c_float), ("rays", C.c_uint64), ("launches", C.c_uint32),
                 ("reserved", C.c_uint32)]
@@ -93,6 +97,9 @@ CUDA_API = {
     "wx_ipc_open": (C.c_int, [vp, C.c_int, u8p, C.POINTER(vp)]),
     "wx_ipc_close": (C.c_int, [vp, C.c_int, vp]),
     "wx_shard_rows": (C.c_int, [C.c_uint32, C.POINTER(WxShard), vp]),
+    "wx_compute_sdf": (C.c_int, [vp, C.POINTER(WxTreeDesc), vp, vp, vp, C.c_uint32, C.POINTER(WxSdfInfo)]),
+    "wx_capture_srgb": (C.c_int, [vp, C.c_uint32, C.c_uint32, C.c_uint32, vp]),
+    "wx_srgb_table": (C.c_int, [vp]),
 }
 f3, u3, i3 = C.POINTER(C.c_float), C.POINTER(C.c_uint32), C.POINTER(C.c_int32)
 HOST_API = {
@@ -125,6 +132,9 @@ HOST_API = {
     "wxh_renderer_change_vdb_model_file": (C.c_int, [vp, C.c_char_p, C.c_char_p]),
     "wxh_renderer_set_options": (C.c_int, [vp, C.c_uint32, u3, f3, f3, C.c_float]),
     "wxh_renderer_render": (C.c_int, [vp, f3, f3, f3, C.c_float, C.c_float, vp]),
+    "wxh_renderer_set_sdf_on_gpu": (C.c_int, [vp, C.c_int]),
+    "wxh_renderer_last_sdf": (None, [vp, C.POINTER(WxSdfInfo)]),
+    "wxh_flat_compute_sdf_gpu": (C.c_int, [vp, vp, C.POINTER(WxSdfInfo)]),
     "wxh_renderer_context": (vp, [vp]),
     "wxh_renderer_tree": (vp, [vp]),
 }

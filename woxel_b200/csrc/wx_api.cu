@@ -6,6 +6,7 @@
 // pipelines, layouts and textures on every redraw): buffers, streams and events live in the context.
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -46,6 +47,9 @@ struct DeviceSlot {
 struct FrameBuffers {  // device[0]-resident outputs of wx_render
   uint8_t* rgba = nullptr;
   size_t rgba_bytes = 0;
+  size_t rgba_valid = 0;  // bytes of the last rendered frame(s)
+  uint8_t* rgb = nullptr;  // wx_capture_srgb staging
+  size_t rgb_bytes = 0;
   void* aov[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   size_t aov_bytes[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 };
@@ -180,6 +184,7 @@ static void free_frame_buffers(WxContext* ctx) {
   if (ctx->dev.empty()) return;
   (void)cudaSetDevice(ctx->dev[0].id);
   if (ctx->fb.rgba) (void)cudaFree(ctx->fb.rgba);
+  if (ctx->fb.rgb) (void)cudaFree(ctx->fb.rgb);
   for (auto& p : ctx->fb.aov)
     if (p) (void)cudaFree(p);
   ctx->fb = FrameBuffers();
@@ -391,6 +396,33 @@ extern "C" int wx_tree_upload(WxContext* ctx, const WxTreeDesc* d, WxTree** out)
   }
   (void)cudaSetDevice(ctx->dev[0].id);
   *out = t;
+  return WX_OK;
+}
+
+extern "C" int wx_compute_sdf(WxContext* ctx, const WxTreeDesc* d, uint32_t* tab5_out, uint32_t* tab4_out, void* tab3_out,
+                              uint32_t tab3_elem_bytes, WxSdfInfo* info) {
+  if (!ctx || !d) return fail(ctx, WX_ERR_INVALID_ARGUMENT, "wx_compute_sdf: null argument");
+  if ((d->n5 && (!d->origins || !d->kids5 || !d->tab5 || !tab5_out)) || (d->n4 && (!d->kids4 || !d->tab4 || !tab4_out)) ||
+      (d->n3 && (!d->vals3 || !tab3_out)))
+    return fail(ctx, WX_ERR_INVALID_ARGUMENT, "wx_compute_sdf: missing array");
+  if (tab3_elem_bytes != 1 && tab3_elem_bytes != 4) return fail(ctx, WX_ERR_INVALID_ARGUMENT, "wx_compute_sdf: tab3_elem_bytes must be 1 or 4");
+  // child indices must be in range: the sweeps follow them
+  for (size_t i = 0; i < (size_t)d->n5 * 32768; ++i)
+    if (bit(d->kids5, i) && d->tab5[i] >= d->n4) return fail(ctx, WX_ERR_BAD_TREE, "wx_compute_sdf: N5 child index out of range");
+  for (size_t i = 0; i < (size_t)d->n4 * 4096; ++i)
+    if (bit(d->kids4, i) && d->tab4[i] >= d->n3) return fail(ctx, WX_ERR_BAD_TREE, "wx_compute_sdf: N4 child index out of range");
+  DeviceSlot& d0 = ctx->dev[0];
+  WX_CUDA(ctx, cudaSetDevice(d0.id));
+  const auto t0 = std::chrono::steady_clock::now();
+  uint32_t r[4] = {0, 0, 0, 0};
+  float ms = 0.f;
+  WX_CUDA(ctx, compute_sdf_device(*d, tab5_out, tab4_out, tab3_out, tab3_elem_bytes, r, &ms, d0.stream));
+  if (info) {
+    info->max_dist[0] = r[0], info->max_dist[1] = r[1], info->max_dist[2] = r[2], info->reserved = 0;
+    info->device_ms = ms;
+    info->total_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  }
+  if (r[3]) return fail(ctx, WX_ERR_UNSUPPORTED, "wx_compute_sdf: a leaf distance does not fit the requested element size");
   return WX_OK;
 }
 
@@ -683,6 +715,7 @@ extern "C" int wx_render(WxContext* ctx, const WxTree* tree, const WxState* stat
   WX_CUDA(ctx, cudaEventRecord(ctx->total1, d0.stream));
   WX_CUDA(ctx, cudaStreamSynchronize(d0.stream));
   ctx->total_pending = true;
+  ctx->fb.rgba_valid = npix * 4;
   ctx->info = WxRenderInfo{};
   ctx->info.launches = launches;
   ctx->info.rays = (uint64_t)(width / 8 * 8) * (height / 4 * 4) * n_states;
@@ -701,6 +734,26 @@ extern "C" int wx_shard_rows(uint32_t height, const WxShard* shard, uint8_t* row
     const uint64_t first = (uint64_t)(k * shard->count + shard->index) * shard->band_rows;
     for (uint64_t y = first; y < first + shard->band_rows && y < height; ++y) row_mask_out[y] = 1;
   }
+  return WX_OK;
+}
+
+extern "C" int wx_srgb_table(uint8_t table_out[256]) {
+  if (!table_out) return WX_ERR_INVALID_ARGUMENT;
+  build_srgb_lut(table_out);
+  return WX_OK;
+}
+
+extern "C" int wx_capture_srgb(WxContext* ctx, uint32_t n_states, uint32_t width, uint32_t height, uint8_t* rgb_out) {
+  if (!ctx || !rgb_out) return fail(ctx, WX_ERR_INVALID_ARGUMENT, "wx_capture_srgb: null argument");
+  const size_t npix = (size_t)n_states * width * height;
+  if (npix == 0 || npix * 4 != ctx->fb.rgba_valid) return fail(ctx, WX_ERR_INVALID_ARGUMENT, "wx_capture_srgb: no frame of that size was rendered last");
+  DeviceSlot& d0 = ctx->dev[0];
+  WX_CUDA(ctx, cudaSetDevice(d0.id));
+  int rc = ensure(ctx, (void**)&ctx->fb.rgb, &ctx->fb.rgb_bytes, npix * 3 + 16);
+  if (rc) return rc;
+  WX_CUDA(ctx, launch_srgb_rgb8(ctx->fb.rgba, ctx->fb.rgb, npix, d0.stream));
+  WX_CUDA(ctx, cudaMemcpyAsync(rgb_out, ctx->fb.rgb, npix * 3, cudaMemcpyDeviceToHost, d0.stream));
+  WX_CUDA(ctx, cudaStreamSynchronize(d0.stream));
   return WX_OK;
 }
 

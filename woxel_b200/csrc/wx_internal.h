@@ -16,4 +16,13 @@ inline uint32_t shard_own_bands(uint32_t height, uint32_t index, uint32_t count,
 cudaError_t launch_raycast(RenderParams& P, uint32_t n_cams, uint32_t render_mode, cudaStream_t stream, uint32_t* launches,
                            uint32_t* work_counter, uint32_t resident_ctas);
 constexpr uint32_t kCtasPerSm = 9;
+// RGBA8 (linear) -> RGB8 through recorder.rs' linear_to_srgb; rgba_dev must be 16-byte aligned, rgb_dev 4-byte aligned.
+cudaError_t launch_srgb_rgb8(const uint8_t* rgba_dev, uint8_t* rgb_dev, size_t n_pixels, cudaStream_t stream);
+void build_srgb_lut(uint8_t lut[256]);
+}  // namespace wx
+struct WxTreeDesc;
+namespace wx {
+// wx_sdf.cu: compute_sdf on the current device; info = max distance per level [0..2], values that did not fit [3]
+cudaError_t compute_sdf_device(const WxTreeDesc& d, uint32_t* tab5_out, uint32_t* tab4_out, void* tab3_out, uint32_t tab3_elem_bytes,
+                               uint32_t info[4], float* device_ms, cudaStream_t stream);
 }  // namespace wx

@@ -237,5 +237,13 @@ extern "C" int wxh_renderer_render(WxhRenderer* r, const float eye[3], const flo
     return 0;
   });
 }
+extern "C" int wxh_renderer_set_sdf_on_gpu(WxhRenderer* r, int on) {
+  r->r.sdf_on_gpu = on != 0;
+  return 0;
+}
+extern "C" void wxh_renderer_last_sdf(const WxhRenderer* r, WxSdfInfo* out) { *out = r->r.last_sdf; }
+extern "C" int wxh_flat_compute_sdf_gpu(WxhFlat* f, WxContext* ctx, WxSdfInfo* info) {
+  return guarded([&]() { return render::Renderer::compute_sdf_gpu(ctx, f->f, info) ? 0 : (int)WX_ERR_UNSUPPORTED; });
+}
 extern "C" WxContext* wxh_renderer_context(WxhRenderer* r) { return r->r.context(); }
 extern "C" WxTree* wxh_renderer_tree(WxhRenderer* r) { return r->r.tree(); }

@@ -133,9 +133,34 @@ Renderer::~Renderer() {
   if (ctx_) wx_shutdown(ctx_);
 }
 
+bool Renderer::compute_sdf_gpu(WxContext* ctx, vdb::FlatTree& flat, WxSdfInfo* info) {
+  // narrow (u8) leaf distances first -- what every level set produces -- then u32
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    flat.narrow = attempt == 0;
+    if (flat.narrow) flat.tab3_u8.assign((size_t)flat.n3 * 512, 0), flat.tab3.clear();
+    else flat.tab3.assign((size_t)flat.n3 * 512, 0), flat.tab3_u8.clear();
+    const WxTreeDesc d = flat.desc();
+    void* t3 = flat.narrow ? (void*)flat.tab3_u8.data() : (void*)flat.tab3.data();
+    const int rc = wx_compute_sdf(ctx, &d, flat.tab5.data(), flat.tab4.data(), t3, flat.narrow ? 1 : 4, info);
+    if (rc == WX_OK) return true;
+    if (rc != WX_ERR_UNSUPPORTED) check(ctx, rc, "wx_compute_sdf");
+  }
+  return false;
+}
+
 void Renderer::change_vdb_model(vdb::VDB345& vdb, bool run_compute_sdf) {
-  if (run_compute_sdf) vdb.compute_sdf();
-  const vdb::FlatTree flat = vdb.to_flat();
+  vdb::FlatTree flat;
+  bool swept = false;
+  last_sdf = WxSdfInfo{};
+  if (run_compute_sdf && sdf_on_gpu) {
+    flat = vdb.to_flat();  // topology; the distances are filled in below
+    swept = compute_sdf_gpu(ctx_, flat, &last_sdf);
+    if (!swept) last_sdf = WxSdfInfo{};
+  }
+  if (!swept) {
+    if (run_compute_sdf) vdb.compute_sdf();
+    flat = vdb.to_flat();
+  }
   const WxTreeDesc d = flat.desc();
   WxTree* t = nullptr;
   check(ctx_, wx_tree_upload(ctx_, &d, &t), "wx_tree_upload");

@@ -61,9 +61,16 @@ class Renderer {
   RenderMode render_mode = RenderMode::Diffuse;  // egui_dev.rs:59
   bool show_grid[3] = {false, false, false};     // egui_dev.rs:60
   SunSettings sun_settings;                      // egui_dev.rs:61
+  // compute_sdf (wgpu_context.rs:104, :513) runs on the GPU (wx_compute_sdf, identical values); the host sweep
+  // VDB345::compute_sdf takes over when a distance does not fit that path, or when this is false
+  bool sdf_on_gpu = true;
+  WxSdfInfo last_sdf{};    // timing of the last GPU sweep (device_ms == 0: the host sweep ran)
 
   WxContext* context() const { return ctx_; }
   WxTree* tree() const { return tree_; }
+
+  // Fills the distances of `flat` (tab5 / tab4 tiles, tab3) on the GPU.  False: not representable there.
+  static bool compute_sdf_gpu(WxContext* ctx, vdb::FlatTree& flat, WxSdfInfo* info);
 
  private:
   uint32_t width_, height_;

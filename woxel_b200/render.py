@@ -120,6 +120,25 @@ class Context:
                                              C.byref(a) if a is not None else None))
         return rgba, aovs
 
+    def compute_sdf(self, flat_or_desc, narrow_leaves: bool = False):
+        """wx_compute_sdf: VDB345::compute_sdf (vdb345.rs:290-628) on the GPU for a flat tree (its tile / voxel
+        distances are ignored on input).  Returns (tab5, tab4, tab3, WxSdfInfo) in the layout of FlatTree."""
+        d = flat_or_desc.desc if hasattr(flat_or_desc, "desc") else flat_or_desc
+        tab5 = np.empty((d.n5, 32768), np.uint32)
+        tab4 = np.empty((d.n4, 4096), np.uint32)
+        tab3 = np.empty((d.n3, 512), np.uint8 if narrow_leaves else np.uint32)
+        info = _ffi.WxSdfInfo()
+        self.check(_ffi.cuda_lib().wx_compute_sdf(self._h, C.byref(d), tab5.ctypes.data, tab4.ctypes.data, tab3.ctypes.data,
+                                                  tab3.dtype.itemsize, C.byref(info)))
+        return tab5, tab4, tab3, info
+
+    def capture_srgb(self, n_states: int, width: int, height: int) -> np.ndarray:
+        """wx_capture_srgb: the frame(s) of the last render() as RGB8 after the reference's linear_to_srgb
+        (recorder.rs:20-37, :132-140).  Returns uint8 [n, H, W, 3]."""
+        rgb = np.empty((n_states, height, width, 3), np.uint8)
+        self.check(_ffi.cuda_lib().wx_capture_srgb(self._h, n_states, width, height, rgb.ctypes.data))
+        return rgb
+
     def render_device(self, tree: "Tree", states, width: int, height: int, rgba_ptr: int, aov_ptrs: dict | None = None,
                       shard: tuple | None = None, stream: int = 0, device_index: int = 0):
         """wx_render_device: asynchronous, device-resident output (pointers are raw device addresses)."""
@@ -201,12 +220,19 @@ class Renderer:
         if rc != 0:
             raise WxError(rc, _ffi.host_lib().wxh_last_error().decode())
 
-    def change_vdb_model(self, vdb_or_path, grid: str | None = None, compute_sdf: bool = True):
-        """wgpu_context.rs:506-573."""
+    def change_vdb_model(self, vdb_or_path, grid: str | None = None, compute_sdf: bool = True, sdf_on_gpu: bool = True):
+        """wgpu_context.rs:506-573.  compute_sdf runs on the GPU (identical values) unless sdf_on_gpu is False."""
+        _ffi.host_lib().wxh_renderer_set_sdf_on_gpu(self._h, 1 if sdf_on_gpu else 0)
         if isinstance(vdb_or_path, VDB345):
             self._check(_ffi.host_lib().wxh_renderer_change_vdb_model(self._h, vdb_or_path._h, 1 if compute_sdf else 0))
         else:
             self._check(_ffi.host_lib().wxh_renderer_change_vdb_model_file(self._h, str(vdb_or_path).encode(), grid.encode()))
+
+    @property
+    def last_sdf(self) -> _ffi.WxSdfInfo:
+        info = _ffi.WxSdfInfo()
+        _ffi.host_lib().wxh_renderer_last_sdf(self._h, C.byref(info))
+        return info
 
     def render(self, scene: Scene) -> np.ndarray:
         """wgpu_context.rs:207-292: one frame, rgba8 [H, W, 4]."""
@@ -221,5 +247,14 @@ class Renderer:
         return out
 
 
+def write_ppm(path: str, rgb: np.ndarray) -> None:
+    """Binary PPM (P6) of an RGB8 frame [H, W, 3]: the recorder's frame dump without ffmpeg (recorder.rs:67-105)."""
+    rgb = np.ascontiguousarray(rgb, np.uint8)
+    assert rgb.ndim == 3 and rgb.shape[2] == 3
+    with open(path, "wb") as f:
+        f.write(b"P6\n%d %d\n255\n" % (rgb.shape[1], rgb.shape[0]))
+        f.write(rgb.tobytes())
+
+
 __all__ = ["WxError", "RenderMode", "SunSettings", "ComputeState", "Context", "Tree", "Renderer", "make_desc",
-           "VdbReader", "AOV_SPEC"]
+           "VdbReader", "AOV_SPEC", "write_ppm"]

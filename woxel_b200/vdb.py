@@ -88,6 +88,17 @@ class FlatTree:
         buf = (C.c_uint8 * (n * np.dtype(dtype).itemsize)).from_address(ptr)
         return np.frombuffer(buf, dtype=dtype).reshape(shape)  # view: valid while self lives
 
+    def compute_sdf_gpu(self, ctx):
+        """Fill this flat tree's distances with wx_compute_sdf (take the flat tree BEFORE VDB345.compute_sdf).
+        Returns the WxSdfInfo; raises WxError(-6) when a distance does not fit the GPU path."""
+        from .render import WxError
+        info = _ffi.WxSdfInfo()
+        rc = _ffi.host_lib().wxh_flat_compute_sdf_gpu(self._h, ctx._h, C.byref(info))
+        if rc != 0:
+            raise WxError(rc, _ffi.host_lib().wxh_last_error().decode())
+        _ffi.host_lib().wxh_flat_desc(self._h, C.byref(self.desc))  # tab3 may have moved (u8 <-> u32)
+        return info
+
     @property
     def origins(self):
         return self._arr(self.desc.origins, np.int32, (self.n5, 3))
