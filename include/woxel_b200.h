@@ -148,7 +148,7 @@ int wx_tree_info(const WxTree *tree, WxTreeInfo *info);
 
 typedef struct WxSdfInfo {
   uint32_t max_dist[3]; /* largest distance written to tab5 / tab4 / tab3 */
-  uint32_t reserved;
+  uint32_t rounds;      /* relaxation rounds run over all levels and both passes */
   float device_ms;      /* device time of the sweeps (CUDA events), without the host<->device copies */
   float total_ms;       /* wall time of the call */
 } WxSdfInfo;

@@ -55,7 +55,7 @@ class WxTreeInfo(C.Structure):
 
 
 class WxSdfInfo(C.Structure):
-    _fields_ = [("max_dist", C.c_uint32 * 3), ("reserved", C.c_uint32), ("device_ms", C.c_float), ("total_ms", C.c_float)]
+    _fields_ = [("max_dist", C.c_uint32 * 3), ("rounds", C.c_uint32), ("device_ms", C.c_float), ("total_ms", C.c_float)]
 
 
 class WxRenderInfo(C.Structure):

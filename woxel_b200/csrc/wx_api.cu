@@ -414,11 +414,11 @@ extern "C" int wx_compute_sdf(WxContext* ctx, const WxTreeDesc* d, uint32_t* tab
   DeviceSlot& d0 = ctx->dev[0];
   WX_CUDA(ctx, cudaSetDevice(d0.id));
   const auto t0 = std::chrono::steady_clock::now();
-  uint32_t r[4] = {0, 0, 0, 0};
+  uint32_t r[5] = {0, 0, 0, 0, 0};
   float ms = 0.f;
   WX_CUDA(ctx, compute_sdf_device(*d, tab5_out, tab4_out, tab3_out, tab3_elem_bytes, r, &ms, d0.stream));
   if (info) {
-    info->max_dist[0] = r[0], info->max_dist[1] = r[1], info->max_dist[2] = r[2], info->reserved = 0;
+    info->max_dist[0] = r[0], info->max_dist[1] = r[1], info->max_dist[2] = r[2], info->rounds = r[4];
     info->device_ms = ms;
     info->total_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
   }

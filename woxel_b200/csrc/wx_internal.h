@@ -22,7 +22,7 @@ void build_srgb_lut(uint8_t lut[256]);
 }  // namespace wx
 struct WxTreeDesc;
 namespace wx {
-// wx_sdf.cu: compute_sdf on the current device; info = max distance per level [0..2], values that did not fit [3]
+// wx_sdf.cu: compute_sdf on the current device; info = max distance per level [0..2], values that did not fit [3], relaxation rounds [4]
 cudaError_t compute_sdf_device(const WxTreeDesc& d, uint32_t* tab5_out, uint32_t* tab4_out, void* tab3_out, uint32_t tab3_elem_bytes,
-                               uint32_t info[4], float* device_ms, cudaStream_t stream);
+                               uint32_t info[5], float* device_ms, cudaStream_t stream);
 }  // namespace wx

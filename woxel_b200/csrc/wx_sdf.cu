@@ -4,19 +4,23 @@
 // origin, slots ascending, recursively); every tile / inactive voxel takes min(self, neighbour + 1)
 // over the 13 already-visited neighbours of its own level, a neighbour that is a child, an active
 // voxel, of another level or missing contributes 1, and the values read are whatever the sweep has
-// produced so far (the result depends on the traversal order).  Three observations
-// turn that into a parallel algorithm with identical results:
+// produced so far (the result depends on the traversal order).  What makes it parallel
+// without changing a value:
 //   (1) the three levels never read each other's distances, so each level is swept on its own;
-//   (2) the value a slot ends a pass with is a pure function of the pass-final values of its 13
-//       neighbours that precede it in the pass and of the pass-initial values of the others --
-//       inside a node "precedes" is lexicographic (x, y, z) order, and 4x + 2y + z is smaller for
-//       all 13 neighbours, so the slots of one node are swept in 7(DIM-1)+1 wavefronts;
-//   (3) between nodes "precedes" is the DFS index.  One CTA per node takes a ticket (nodes are
-//       handed out in pass order, so everything a CTA waits for is running or done), waits for
-//       the <= 13 neighbour nodes that precede it, reads their final values (and the pass-initial
-//       values of the neighbours that follow it, from the other buffer), sweeps, publishes.
-// Forward results live in F, backward (final) results in B; the forward pass' initial value is the
-// constant MAX-1 of vdb345.rs:300-319.
+//   (2) the value a slot ends a pass with is a pure function of the pass-FINAL values of those of its
+//       13 neighbours that precede it in the pass and of the pass-INITIAL values of the others.
+//       "Precedes" is lexicographic (x, y, z) order inside a node and the DFS index between nodes, so
+//       a pass is the unique solution of a recurrence over a DAG:
+//           v(c) = min(init(c), 1 + min over the 13 n of (n precedes c ? v(n) : init(n)))
+//       (init = MAX-1 in the forward pass, the forward result in the backward pass; seeds are 0);
+//   (3) that solution is also the limit of relaxing all nodes at once from any upper bound: every
+//       relaxed value stays an upper bound, and a value d is exact after at most d rounds because its
+//       derivation chain has d links.  Distances are small (<= 16 on every scene here), so a pass is
+//       a handful of rounds in which every node is independent: one CTA per node loads the node plus
+//       a one-cell halo of its 26 neighbours into shared memory, sweeps it exactly in 7(DIM-1)+1
+//       wavefronts (4x + 2y + z is smaller for all 13 neighbours) and writes it back; rounds repeat
+//       until none changes a value.
+// Forward results live in F, backward (final) results in B.
 #include <algorithm>
 #include <cstring>
 #include <vector>
@@ -112,9 +116,7 @@ struct LevelPass {
   const int32_t* nb;       // [n][27]
   V* F;                    // forward results  [n][SLOTS]
   V* B;                    // backward results [n][SLOTS]
-  uint32_t* done;          // [n]: tag of the last pass that finished the node
-  uint32_t* ticket;        // zeroed before the launch
-  uint32_t tag;            // unique per launch
+  uint32_t* changed;       // set when a round lowers a value
   int backward;
 };
 
@@ -133,27 +135,12 @@ __global__ void sweep_kernel(const LevelPass<V> L) {
   constexpr V INF = Inf<V>::v;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   V* halo = reinterpret_cast<V*>(smem_raw);  // [H][H][H], index ((x+1)*H + (y+1))*H + (z+1)
-  __shared__ uint32_t s_node;
   __shared__ int32_t s_nb[27];
+  __shared__ uint32_t s_changed;
   const int tid = threadIdx.x;
-
-  if (tid == 0) {
-    const uint32_t t = atomicAdd(L.ticket, 1u);
-    s_node = L.backward ? L.n - 1u - t : t;
-  }
-  __syncthreads();
-  const uint32_t k = s_node;
-  if (tid < 27) {
-    const int32_t j = L.nb[(size_t)k * 27 + tid];
-    s_nb[tid] = j;
-    // wait for the neighbours that precede this node in the pass
-    const bool precedes = j >= 0 && (L.backward ? (uint32_t)j > k : (uint32_t)j < k);
-    if (precedes) {
-      const volatile uint32_t* flag = L.done + j;
-      while (*flag != L.tag) __nanosleep(64);
-      __threadfence();
-    }
-  }
+  const uint32_t k = blockIdx.x;
+  if (tid < 27) s_nb[tid] = L.nb[(size_t)k * 27 + tid];
+  if (tid == 0) s_changed = 0u;
   __syncthreads();
 
   // ---- fill the halo cube --------------------------------------------------------------------
@@ -173,8 +160,8 @@ __global__ void sweep_kernel(const LevelPass<V> L) {
         v = L.backward ? L.F[(size_t)k * SLOTS + o] : INF;  // own slots start from the previous pass
       } else {
         const bool precedes = L.backward ? (uint32_t)j > k : (uint32_t)j < k;
-        if (precedes) v = ld_cg(cur_buf + (size_t)j * SLOTS + o);           // final value of this pass
-        else v = L.backward ? ld_cg(L.F + (size_t)j * SLOTS + o) : INF;     // not swept yet in this pass
+        if (precedes) v = ld_cg(cur_buf + (size_t)j * SLOTS + o);           // this pass' value so far (an upper bound; exact at the fixed point)
+        else v = L.backward ? L.F[(size_t)j * SLOTS + o] : INF;             // follows this node: its pass-initial value
       }
     }
     halo[c] = v;
@@ -216,17 +203,26 @@ __global__ void sweep_kernel(const LevelPass<V> L) {
     __syncthreads();
   }
 
-  // ---- publish ----------------------------------------------------------------------------------
+  // ---- write back; report whether this round still lowered something ------------------------------
+  bool lowered = false;
   for (uint32_t o = tid; o < SLOTS; o += blockDim.x) {
     const int x = (int)(o >> (2 * LOG2D)), y = (int)((o >> LOG2D) & (DIM - 1)), z = (int)(o & (DIM - 1));
-    cur_buf[(size_t)k * SLOTS + o] = halo[((x + 1) * H + (y + 1)) * H + (z + 1)];
+    const V v = halo[((x + 1) * H + (y + 1)) * H + (z + 1)];
+    V* dst = cur_buf + (size_t)k * SLOTS + o;
+    if (*dst != v) {
+      *dst = v;
+      lowered = true;
+    }
   }
-  __threadfence();
+  if (lowered) s_changed = 1u;
   __syncthreads();
-  if (tid == 0) {
-    volatile uint32_t* flag = L.done + k;
-    *flag = L.tag;
-  }
+  if (tid == 0 && s_changed) *L.changed = 1u;
+}
+
+template <class V>
+__global__ void fill_kernel(V* p, size_t n, V v) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
 }
 
 // distances -> the reference's table: child index where the child bit is set, else the distance (u32)
@@ -271,9 +267,11 @@ __global__ void merge_leaf_kernel(const uint64_t* vals3, const uint16_t* dist, s
     }                                           \
   } while (0)
 
+// One pass of one level: rounds of the relaxation kernel until a round changes nothing.
 template <int LOG2D, class V>
-static cudaError_t run_pass(sdf::LevelPass<V> L, cudaStream_t stream) {
+static cudaError_t run_pass(sdf::LevelPass<V> L, cudaStream_t stream, uint32_t* rounds) {
   constexpr int DIM = 1 << LOG2D, H = DIM + 2;
+  constexpr size_t SLOTS = (size_t)1 << (3 * LOG2D);
   const size_t smem = (size_t)H * H * H * sizeof(V);
   const int threads = std::max(DIM * DIM, 32);
   static bool attr_done = false;
@@ -283,16 +281,36 @@ static cudaError_t run_pass(sdf::LevelPass<V> L, cudaStream_t stream) {
     attr_done = true;
   }
   if (L.n == 0) return cudaSuccess;
-  cudaError_t e = cudaMemsetAsync(L.ticket, 0, sizeof(uint32_t), stream);
+  const size_t cells = (size_t)L.n * SLOTS;
+  cudaError_t e;
+  // upper bound the relaxation starts from: MAX-1 (forward), the forward result (backward)
+  if (L.backward) {
+    e = cudaMemcpyAsync(L.B, L.F, cells * sizeof(V), cudaMemcpyDeviceToDevice, stream);
+  } else {
+    sdf::fill_kernel<V><<<(unsigned)((cells + 255) / 256), 256, 0, stream>>>(L.F, cells, sdf::Inf<V>::v);
+    e = cudaGetLastError();
+  }
   if (e != cudaSuccess) return e;
-  sdf::sweep_kernel<LOG2D, V><<<L.n, threads, smem, stream>>>(L);
-  return cudaGetLastError();
+  for (uint32_t r = 0; r < 100000u; ++r) {
+    e = cudaMemsetAsync(L.changed, 0, sizeof(uint32_t), stream);
+    if (e != cudaSuccess) return e;
+    sdf::sweep_kernel<LOG2D, V><<<L.n, threads, smem, stream>>>(L);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    uint32_t changed = 0;
+    e = cudaMemcpyAsync(&changed, L.changed, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    if (e != cudaSuccess) return e;
+    ++*rounds;
+    if (!changed) break;
+  }
+  return cudaSuccess;
 }
 
 // Everything on `stream` of the current device.  Host arrays in, host arrays out (tab3_out: u8 when
-// tab3_elem_bytes == 1, else u32).  info: [0..2] max distance per level, [3] values that did not fit.
+// tab3_elem_bytes == 1, else u32).  info: [0..2] max distance per level, [3] values that did not fit, [4] rounds.
 cudaError_t compute_sdf_device(const WxTreeDesc& d, uint32_t* tab5_out, uint32_t* tab4_out, void* tab3_out, uint32_t tab3_elem_bytes,
-                               uint32_t info[4], float* device_ms, cudaStream_t stream) {
+                               uint32_t info[5], float* device_ms, cudaStream_t stream) {
   std::vector<void*> allocs;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   auto cleanup = [&]() {
@@ -313,7 +331,7 @@ cudaError_t compute_sdf_device(const WxTreeDesc& d, uint32_t* tab5_out, uint32_t
   const size_t s5 = (size_t)d.n5 * 32768, s4 = (size_t)d.n4 * 4096, s3 = (size_t)d.n3 * 512;
   int32_t *org5, *org4, *org3, *nb5, *nb4, *nb3;
   uint64_t *kids5, *kids4, *vals3;
-  uint32_t *tab5, *tab4, *F5, *B5, *F4, *B4, *done, *misc, *out5, *out4;
+  uint32_t *tab5, *tab4, *F5, *B5, *F4, *B4, *misc, *out5, *out4;
   uint16_t *F3, *B3;
   void* out3;
   SDF_CUDA(cudaEventCreate(&ev0));
@@ -338,10 +356,7 @@ cudaError_t compute_sdf_device(const WxTreeDesc& d, uint32_t* tab5_out, uint32_t
   SDF_CUDA(dalloc((void**)&out5, s5 * 4));
   SDF_CUDA(dalloc((void**)&out4, s4 * 4));
   SDF_CUDA(dalloc(&out3, s3 * (tab3_elem_bytes == 1 ? 1 : 4)));
-  const size_t n_done = (size_t)d.n5 + d.n4 + d.n3;
-  SDF_CUDA(dalloc((void**)&done, n_done * 4));
-  SDF_CUDA(dalloc((void**)&misc, 64));  // [0] ticket, [4..6] max per level, [7] bad
-  SDF_CUDA(cudaMemsetAsync(done, 0, n_done * 4 + 0, stream));
+  SDF_CUDA(dalloc((void**)&misc, 64));  // [0] changed flag, [6] max leaf distance, [7] values that do not fit
   SDF_CUDA(cudaMemsetAsync(misc, 0, 64, stream));
   SDF_CUDA(cudaEventRecord(ev0, stream));
 
@@ -354,14 +369,14 @@ cudaError_t compute_sdf_device(const WxTreeDesc& d, uint32_t* tab5_out, uint32_t
   if (d.n3) sdf::neighbours_kernel<<<blocks((size_t)d.n3 * 27), 256, 0, stream>>>(T, 3, org3, d.n3, 8, nb3);
   SDF_CUDA(cudaGetLastError());
 
-  uint32_t tag = 1;
+  uint32_t rounds = 0;
   for (int pass = 0; pass < 2; ++pass) {
-    sdf::LevelPass<uint32_t> L5{d.n5, kids5, nb5, F5, B5, done, misc, tag++, pass};
-    SDF_CUDA((run_pass<5, uint32_t>(L5, stream)));
-    sdf::LevelPass<uint32_t> L4{d.n4, kids4, nb4, F4, B4, done + d.n5, misc, tag++, pass};
-    SDF_CUDA((run_pass<4, uint32_t>(L4, stream)));
-    sdf::LevelPass<uint16_t> L3{d.n3, vals3, nb3, F3, B3, done + d.n5 + d.n4, misc, tag++, pass};
-    SDF_CUDA((run_pass<3, uint16_t>(L3, stream)));
+    sdf::LevelPass<uint32_t> L5{d.n5, kids5, nb5, F5, B5, misc, pass};
+    SDF_CUDA((run_pass<5, uint32_t>(L5, stream, &rounds)));
+    sdf::LevelPass<uint32_t> L4{d.n4, kids4, nb4, F4, B4, misc, pass};
+    SDF_CUDA((run_pass<4, uint32_t>(L4, stream, &rounds)));
+    sdf::LevelPass<uint16_t> L3{d.n3, vals3, nb3, F3, B3, misc, pass};
+    SDF_CUDA((run_pass<3, uint16_t>(L3, stream, &rounds)));
   }
   if (s5) sdf::merge_internal_kernel<<<blocks(s5), 256, 0, stream>>>(kids5, tab5, B5, s5, 15, out5);
   if (s4) sdf::merge_internal_kernel<<<blocks(s4), 256, 0, stream>>>(kids4, tab4, B4, s4, 12, out4);
@@ -384,7 +399,7 @@ cudaError_t compute_sdf_device(const WxTreeDesc& d, uint32_t* tab5_out, uint32_t
     if (!((d.kids5[i >> 6] >> (i & 63)) & 1ull) && tab5_out[i] != 0xFFFFFFFEu) m5 = std::max(m5, tab5_out[i]);
   for (size_t i = 0; i < s4; ++i)
     if (!((d.kids4[i >> 6] >> (i & 63)) & 1ull) && tab4_out[i] != 0xFFFFFFFEu) m4 = std::max(m4, tab4_out[i]);
-  info[0] = m5, info[1] = m4, info[2] = h_misc[6], info[3] = h_misc[7];
+  info[0] = m5, info[1] = m4, info[2] = h_misc[6], info[3] = h_misc[7], info[4] = rounds;
   cleanup();
   return cudaSuccess;
 }
