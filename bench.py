@@ -385,7 +385,8 @@ def main():
             "value_warm_l2": round(world * rays_per_frame / (warm_ms * 1e-3) / 1e6, 1),
             "wall_ms_per_step_incl_flush": round(1e3 * wall / args.steps, 4),
             "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": 256 * world, "d2h_bytes_per_step": frame_bytes * world,
-                    "api": "wx_render (host state in, pinned host RGBA8 out), blocking", "steps": e2e_steps,
+                    "api": "wx_render (host state in, pinned host RGBA8 out), blocking; read-back pipelined over row chunks",
+                    "steps": e2e_steps, "kernel_launches_per_step": int(e2e_info.launches),
                     "last_call_device_ms": {"kernels": round(e2e_info.kernel_ms, 4), "total_incl_readback": round(e2e_info.total_ms, 4)}},
             "gpu_launches": args.steps * world,
             "clocks": clocks, "roofline": roof, "cpu_baseline": cpu_baseline,
