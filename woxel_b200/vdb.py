@@ -78,7 +78,10 @@ class FlatTree:
 
     def __del__(self):
         if getattr(self, "_h", None):
-            _ffi.host_lib().wxh_flat_free(self._h)
+            try:
+                _ffi.host_lib().wxh_flat_free(self._h)
+            except TypeError:  # interpreter teardown: the module globals are already gone
+                pass
             self._h = None
 
     def _arr(self, ptr, dtype, shape):
@@ -147,7 +150,10 @@ class VDB345:
 
     def __del__(self):
         if getattr(self, "_h", None):
-            _ffi.host_lib().wxh_vdb_free(self._h)
+            try:
+                _ffi.host_lib().wxh_vdb_free(self._h)
+            except TypeError:  # interpreter teardown
+                pass
             self._h = None
 
     def set_voxel(self, p, v: int = 1):
