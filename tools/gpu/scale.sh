@@ -1,3 +1,4 @@
+# Weak scaling (bench.py under torchrun) + single-frame strong scaling on every GPU of the box:  gpurun --gpus N -- "bash tools/gpu/scale.sh"
 N=$(nvidia-smi -L | wc -l)
 echo "GPUs: $N"
 timeout 300 python -m pytest tests -m gpu -x -q -k "multi_device" 2>&1 | tail -2
