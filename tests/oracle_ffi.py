@@ -13,7 +13,9 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_DIR = os.path.join(ROOT, "oracle")
-LIB_PATH = os.path.join(ORACLE_DIR, "libwxo.so")
+# WXO_VARIANT=fma loads the FMA-contracted sensitivity build (oracle/Makefile); the default is the strict-IEEE oracle
+_VARIANT = "libwxo_fma.so" if os.environ.get("WXO_VARIANT") == "fma" else "libwxo.so"
+LIB_PATH = os.path.join(ORACLE_DIR, _VARIANT)
 
 EP_OFFS, EP_LEAF, EP_INNR5, EP_INNR4, EP_ROOT, EP_BKGR = range(6)
 
@@ -22,7 +24,7 @@ def build_oracle(force: bool = False) -> str:
     srcs = [os.path.join(ORACLE_DIR, f) for f in os.listdir(ORACLE_DIR) if f.endswith((".c", ".h")) or f == "Makefile"]
     stale = force or not os.path.exists(LIB_PATH) or any(os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in srcs)
     if stale:
-        subprocess.run(["make", "-C", ORACLE_DIR, "libwxo.so"], check=True, capture_output=True)
+        subprocess.run(["make", "-C", ORACLE_DIR, _VARIANT], check=True, capture_output=True)
     return LIB_PATH
 
 
