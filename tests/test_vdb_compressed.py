@@ -1,0 +1,111 @@
+"""The .vdb reader on compressed files: zlib and Blosc(LZ4) blocks, with and without the active
+mask, half and full floats.  The shipped assets exercise none of this (compression flag 0x2 only), so the files are
+made by tests/vdb_writer.py -- a writer derived from the format the reference's READER expects (read.rs), with a
+from-scratch c-blosc 1.x / LZ4 encoder.  Product reader and oracle reader are independent implementations; both must
+recover exactly the voxels that were written.  The reference decodes Blosc through the c-blosc C library
+(blosc-src 0.2.1, not vendored); the oracle has no such decoder and must say so (WXO_ERR_BLOSC)."""
+import numpy as np
+import pytest
+
+import oracle_ffi as O
+import scenes
+import vdb_writer as V
+import woxel_b200 as W
+
+
+def sample_voxels(seed=3):
+    rng = np.random.default_rng(seed)
+    pts = [rng.integers(0, 8, size=(200, 3)) + base for base in ([0, 0, 0], [8, 0, 0], [120, 120, 120], [128, 0, 0], [-8, -8, -8], [-4096, 16, 24],
+                                                                  [4000, 4000, 4000])]
+    dense = np.stack(np.meshgrid(np.arange(16, 24), np.arange(16, 24), np.arange(16, 24), indexing="ij"), -1).reshape(-1, 3)  # a full leaf
+    pts = np.unique(np.concatenate(pts + [dense]), axis=0)
+    vals = rng.uniform(-3, 3, len(pts)).astype(np.float32)
+    return pts.astype(np.int32), vals
+
+
+def expected_bits(vals, half):
+    if half:
+        h = vals.astype(np.float16).view(np.uint16).astype(np.uint32)
+        return ((h >> 8) << 16) | ((h & 255) << 24)  # from_f16_bites, read.rs:635-642: [0, 0, b0, b1] little-endian
+    return vals.astype(np.float32).view(np.uint32)
+
+
+CASES = [(V.NONE, "none"), (V.ACTIVE_MASK, "mask"), (V.ZIP, "zip"), (V.ZIP | V.ACTIVE_MASK, "zip+mask"), (V.BLOSC, "blosc"),
+         (V.BLOSC | V.ACTIVE_MASK, "blosc+mask")]
+
+
+@pytest.mark.parametrize("comp,tag", CASES)
+@pytest.mark.parametrize("half", [True, False])
+@pytest.mark.parametrize("md", [0, 6])
+def test_reader_recovers_written_voxels(tmp_path, comp, tag, half, md):
+    pts, vals = sample_voxels()
+    path = str(tmp_path / f"{tag}.vdb")
+    V.VdbWriter(compression=comp, half_float=half, leaf_metadata=md).write(path, pts, vals)
+    if md == 6 and comp & (V.ZIP | V.BLOSC):  # dense leaf buffers are mostly background: the codecs really ran
+        import os
+        plain = len(V.VdbWriter(compression=comp & V.ACTIVE_MASK, half_float=half, leaf_metadata=md).build(pts, vals))
+        assert os.path.getsize(path) < plain - 500  # (node masks, which dominate this small file, are never compressed)
+    r = W.VdbReader(path)
+    v = r.read_vdb345_grid("ls_test")
+    assert r.info.grid_compression == comp and bool(r.info.is_half_float) == half and r.info.file_voxel_count == len(pts)
+    assert v.count_leaf_values() == len(pts)
+    want = expected_bits(vals, half)
+    for p, wbits in list(zip(pts.tolist(), want.tolist()))[::7]:
+        e = v.get_voxel(p)
+        assert e.kind == "Leaf" and e.value == wbits, (p, e.kind, hex(e.value), hex(wbits))
+    assert v.get_voxel([16 + 8, 16, 16]).kind != "Leaf"  # just outside the dense leaf
+    # the oracle's reader: same tree for everything it supports
+    try:
+        t, info = O.Tree.read(path, "ls_test")
+    except IOError as e:  # the oracle has no Blosc decoder (the reference's is the c-blosc library): WXO_ERR_BLOSC,
+        assert comp & V.BLOSC and "-7" in str(e)  # unless every block of the file happened to be stored raw
+        return
+    assert info.grid_compression == comp
+    o = scenes.OracleScene(t, sdf=False)
+    f = v.to_flat(narrow_leaves=False)
+    assert np.array_equal(f.origins, o.origins)
+    for a, b in ((f.kids5, o.kids5), (f.kids4, o.kids4), (f.vals3, o.vals3)):
+        assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("blocksize", [256, 384, 1024])
+def test_blosc_multi_block_frames(tmp_path, blocksize):
+    """Several blocks per frame, a shorter last block (never split), split and unsplit streams."""
+    pts, vals = sample_voxels(seed=11)
+    path = str(tmp_path / "b.vdb")
+    V.VdbWriter(compression=V.BLOSC, half_float=True, leaf_metadata=6, blosc_blocksize=blocksize).write(path, pts, vals)
+    v = W.VdbReader(path).read_vdb345_grid("ls_test")
+    want = expected_bits(vals, True)
+    for p, wbits in zip(pts.tolist(), want.tolist()):
+        e = v.get_voxel(p)
+        assert e.kind == "Leaf" and e.value == wbits
+
+
+def test_corrupt_blosc_frame_is_an_error_not_a_crash(tmp_path):
+    pts, vals = sample_voxels()
+    raw = bytearray(V.VdbWriter(compression=V.BLOSC | V.ACTIVE_MASK, half_float=True).build(pts, vals))
+    raw[-40] ^= 0xFF  # inside the last leaf's LZ4 stream or its header
+    raw[-90] ^= 0x55
+    p = tmp_path / "bad.vdb"
+    p.write_bytes(bytes(raw))
+    try:
+        v = W.VdbReader(str(p)).read_vdb345_grid("ls_test")
+        assert v.count_leaf_values() == len(pts)  # the damage hit literal bytes only: still a valid stream
+    except W.vdb.VdbError as e:
+        assert e.status in (-101, -107, -108) or "Blosc" in str(e)
+
+
+def test_compressed_model_renders(tmp_path):
+    """zlib file -> product reader -> host sweep -> flat tree == the same voxels set directly."""
+    pts, vals = sample_voxels()
+    path = str(tmp_path / "z.vdb")
+    V.VdbWriter(compression=V.ZIP | V.ACTIVE_MASK, half_float=True).write(path, pts, vals)
+    a = W.VdbReader(path).read_vdb345_grid("ls_test")
+    b = W.VDB345()
+    b.set_voxels(pts)
+    a.compute_sdf(), b.compute_sdf()
+    fa, fb = a.to_flat(False), b.to_flat(False)
+    for k in ("origins", "kids5", "kids4", "vals3", "tab5", "tab4"):
+        assert np.array_equal(getattr(fa, k), getattr(fb, k)), k
+    inactive = ~scenes.bits2d(fa.vals3)
+    assert np.array_equal(fa.tab3[inactive], fb.tab3[inactive])

@@ -129,6 +129,114 @@ void VdbReader::parse_header() {  // read.rs:62-121, :166-212
 
 namespace {
 
+// ---------------------------------------------------------------------------------------------
+// Blosc frames.  The reference hands these to c-blosc (blosc-src 0.2.1: blosc_cbuffer_sizes +
+// blosc_decompress_ctx, read.rs:514-533), a third-party C library that is not in this image.  This is a
+// decoder of the c-blosc 1.x frame written from its published format (README_HEADER.rst, blosc.c):
+//   header  [0] version  [1] versionlz  [2] flags  [3] typesize  [4..8) nbytes  [8..12) blocksize  [12..16) cbytes
+//   flags   bit 0 byte shuffle, bit 1 memcpyed (raw copy follows the header), bit 2 bit shuffle,
+//           bit 4 blocks are not split, bits 5-7 codec (0 BloscLZ, 1 LZ4/LZ4HC, 2 Snappy, 3 zlib, 4 Zstd)
+//   body    int32 offset of every block from the start of the frame; a block is `typesize` streams (when
+//           it is split: typesize <= 16, blocksize / typesize >= 128, not the shorter last block) or one,
+//           each an int32 byte count followed by the codec's output, or by the plain bytes when the count
+//           equals the stream size
+// OpenVDB writes these frames with blosc_compress_ctx(9, shuffle, sizeof(T), ..., "lz4"), so LZ4 (and zlib,
+// through the system library) are decoded; BloscLZ, Snappy, Zstd and bit shuffle report UnsupportedBloscFormat.
+// ---------------------------------------------------------------------------------------------
+bool lz4_decompress_block(const uint8_t* src, size_t n, uint8_t* dst, size_t cap) {
+  size_t i = 0, o = 0;
+  while (i < n) {
+    const uint8_t token = src[i++];
+    size_t ll = token >> 4;
+    if (ll == 15) {
+      uint8_t x;
+      do {
+        if (i >= n) return false;
+        x = src[i++];
+        ll += x;
+      } while (x == 255);
+    }
+    if (ll > n - i || ll > cap - o) return false;
+    memcpy(dst + o, src + i, ll);
+    i += ll, o += ll;
+    if (i >= n) break;  // the last sequence is literals only
+    if (n - i < 2) return false;
+    const size_t off = (size_t)src[i] | ((size_t)src[i + 1] << 8);
+    i += 2;
+    size_t ml = token & 15u;
+    if (ml == 15) {
+      uint8_t x;
+      do {
+        if (i >= n) return false;
+        x = src[i++];
+        ml += x;
+      } while (x == 255);
+    }
+    ml += 4;
+    if (off == 0 || off > o || ml > cap - o) return false;
+    for (size_t k = 0; k < ml; ++k) dst[o + k] = dst[o + k - off];  // byte-wise: matches may overlap their output
+    o += ml;
+  }
+  return o == cap;
+}
+
+std::vector<uint8_t> blosc_decompress(const uint8_t* f, size_t n) {
+  auto bad = [](const char* what) { return VdbError(VdbError::InvalidBloscData, std::string("Blosc frame: ") + what); };
+  auto le32 = [&](size_t at) { return (uint32_t)f[at] | ((uint32_t)f[at + 1] << 8) | ((uint32_t)f[at + 2] << 16) | ((uint32_t)f[at + 3] << 24); };
+  if (n < 16) throw bad("shorter than its header");
+  const uint8_t flags = f[2];
+  const size_t typesize = f[3] ? f[3] : 1, nbytes = le32(4), blocksize = le32(8), cbytes = le32(12);
+  if (cbytes > n) throw bad("cbytes exceeds the stored size");
+  std::vector<uint8_t> out(nbytes);
+  if (nbytes == 0) return out;
+  if (flags & 0x2) {  // memcpyed
+    if (n < 16 + nbytes) throw bad("memcpyed frame is short");
+    memcpy(out.data(), f + 16, nbytes);
+    return out;
+  }
+  if (flags & 0x4) throw VdbError(VdbError::UnsupportedBloscFormat, "Blosc bit shuffle is not supported");
+  const int codec = flags >> 5;
+  if (codec != 1 && codec != 3)
+    throw VdbError(VdbError::UnsupportedBloscFormat, "Blosc codec " + std::to_string(codec) + " is not supported (LZ4 and zlib are)");
+  if (blocksize == 0) throw bad("zero block size");
+  const size_t nblocks = (nbytes + blocksize - 1) / blocksize;
+  if (n < 16 + 4 * nblocks) throw bad("block offsets are cut off");
+  const bool may_split = !(flags & 0x10) && typesize <= 16 && blocksize / typesize >= 128;
+  std::vector<uint8_t> tmp(blocksize);
+  for (size_t b = 0; b < nblocks; ++b) {
+    const size_t bsize = std::min(blocksize, nbytes - b * blocksize);
+    const bool leftover = bsize < blocksize;
+    const size_t nsplits = (may_split && !leftover) ? typesize : 1;
+    const size_t neblock = bsize / nsplits;
+    size_t at = le32(16 + 4 * b);
+    uint8_t* dst = (flags & 0x1) && typesize > 1 ? tmp.data() : out.data() + b * blocksize;
+    for (size_t k = 0; k < nsplits; ++k) {
+      if (at + 4 > n) throw bad("stream header is cut off");
+      const size_t cb = le32(at);
+      at += 4;
+      if (cb > n - at) throw bad("stream is cut off");
+      uint8_t* d = dst + k * neblock;
+      if (cb == neblock) {
+        memcpy(d, f + at, neblock);
+      } else if (codec == 1) {
+        if (!lz4_decompress_block(f + at, cb, d, neblock)) throw bad("corrupt LZ4 stream");
+      } else {
+        uLongf dlen = (uLongf)neblock;
+        if (uncompress(d, &dlen, f + at, (uLong)cb) != Z_OK || dlen != neblock) throw bad("corrupt zlib stream");
+      }
+      at += cb;
+    }
+    if ((flags & 0x1) && typesize > 1) {  // undo the byte shuffle of this block
+      const size_t ne = bsize / typesize;
+      uint8_t* o = out.data() + b * blocksize;
+      for (size_t j = 0; j < typesize; ++j)
+        for (size_t i = 0; i < ne; ++i) o[i * typesize + j] = tmp[j * ne + i];
+      memcpy(o + ne * typesize, tmp.data() + ne * typesize, bsize - ne * typesize);
+    }
+  }
+  return out;
+}
+
 struct NodeValueReader {
   VdbReader::Cursor& c;
   uint32_t version;
@@ -146,7 +254,8 @@ struct NodeValueReader {
         c.bytes(out.data(), out.size());
       } else {
         c.need((size_t)n);
-        if (count > 0) throw VdbError(VdbError::UnsupportedBloscFormat, "Blosc-compressed blocks are not supported yet");
+        out = blosc_decompress(c.b.data() + c.pos, (size_t)n);
+        if (out.size() != count * elem) throw VdbError(VdbError::InvalidBloscData, "Blosc block decodes to an unexpected size");
         c.pos += (size_t)n;
       }
     } else if (gd.compression & ZIP) {
