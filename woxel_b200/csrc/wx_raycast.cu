@@ -55,8 +55,20 @@ __device__ __forceinline__ void shade_and_store(const RenderParams& P, const Pix
 template <int MODE, bool AOV>
 __device__ __forceinline__ void render_pixel(const RenderParams& P, const PixelRef& q) {
   if (!q.in_frame) return;
-  if (!q.dispatched) {  // never dispatched by the reference: zero-initialised texel
-    P.rgba[((size_t)q.cam * P.height + q.y) * P.width + q.x] = make_uchar4(0, 0, 0, 0);
+  if (!q.dispatched) {  // never dispatched by the reference: zero-initialised texel (and zeroed AOVs)
+    const size_t pix = ((size_t)q.cam * P.height + q.y) * P.width + q.x;
+    P.rgba[pix] = make_uchar4(0, 0, 0, 0);
+    if (AOV) {
+      const AovPtrs& a = P.aov;
+      if (a.state) a.state[pix] = 0;
+      if (a.voxel) a.voxel[3 * pix + 0] = a.voxel[3 * pix + 1] = a.voxel[3 * pix + 2] = 0;
+      if (a.leaf) a.leaf[pix] = 0;
+      if (a.level) a.level[pix] = 0;
+      if (a.iters) a.iters[pix] = 0;
+      if (a.depth) a.depth[pix] = 0.f;
+      if (a.mask) a.mask[pix] = 0;
+      if (a.pos) a.pos[3 * pix + 0] = a.pos[3 * pix + 1] = a.pos[3 * pix + 2] = 0.f;
+    }
     return;
   }
   const WxState& s = (P.n_states == 1) ? P.s0 : P.states[q.cam];
