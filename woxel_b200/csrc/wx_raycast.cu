@@ -13,7 +13,7 @@ namespace wx {
 #ifndef WX_CTA_WARPS
 #define WX_CTA_WARPS 4  // 4: CTA = 2x2 warp tiles (16x8 px); 2: 2x1 (16x4 px); 1: one tile (8x4 px)
 #endif
-constexpr int kTileW = WX_CTA_WARPS >= 2 ? 16 : 8, kTileH = WX_CTA_WARPS >= 4 ? 8 : 4;  // CTA footprint in pixels
+constexpr int kTileW = WX_CTA_WARPS >= 2 ? 16 : 8, kTileH = WX_CTA_WARPS >= 8 ? 16 : (WX_CTA_WARPS >= 4 ? 8 : 4);  // CTA footprint in pixels
 constexpr int kThreads = 32 * WX_CTA_WARPS;
 #ifndef WX_MIN_BLOCKS
 #define WX_MIN_BLOCKS (36 / WX_CTA_WARPS)  // resident CTAs per SM the register budget is capped for (36 warps -> 56 registers)
@@ -118,16 +118,22 @@ __device__ __forceinline__ PixelRef pixel_of(const RenderParams& P, uint32_t til
   return q;
 }
 
+#ifndef WX_TILES_PER_GRAB
+#define WX_TILES_PER_GRAB 1  // (measured: 1 -> 0.976 ms, 4 -> 1.20 ms, 16 -> 2.01 ms on the 4K sphere) consecutive tiles (of the 16 of a 32x16-pixel chunk) a warp renders per queue access
+#endif
 template <int MODE, bool AOV>
 __global__ void __launch_bounds__(kThreads, WX_MIN_BLOCKS) raycast_persistent(const __grid_constant__ RenderParams P) {
   const uint32_t lane = threadIdx.x & 31;
   for (;;) {
     uint32_t tile = 0;
-    if (lane == 0) tile = atomicAdd(P.work_counter, 1u);
+    if (lane == 0) tile = atomicAdd(P.work_counter, (uint32_t)WX_TILES_PER_GRAB);
     tile = __shfl_sync(0xffffffffu, tile, 0);
     if (tile >= P.n_chunks * 16u) break;
-    render_pixel<MODE, AOV>(P, pixel_of(P, tile, lane));
-    __syncwarp();
+#pragma unroll 1
+    for (uint32_t k = 0; k < (uint32_t)WX_TILES_PER_GRAB; ++k) {
+      render_pixel<MODE, AOV>(P, pixel_of(P, tile + k, lane));
+      __syncwarp();
+    }
   }
 }
 
@@ -138,10 +144,22 @@ static cudaError_t launch_mode_persistent(const RenderParams& P, unsigned ctas, 
   return cudaGetLastError();
 }
 
+// WX_SMEM_PAD: bytes of (unused) dynamic shared memory per CTA -- an experiment knob that lowers the number of resident
+// CTAs per SM to measure how the kernel responds to occupancy.
+static size_t smem_pad() {
+  static const size_t pad = getenv("WX_SMEM_PAD") ? (size_t)atoi(getenv("WX_SMEM_PAD")) : 0;
+  return pad;
+}
+
 template <int MODE>
 static cudaError_t launch_mode(const RenderParams& P, dim3 grid, cudaStream_t stream) {
-  if (P.has_aov) raycast_kernel<MODE, true><<<grid, kThreads, 0, stream>>>(P);
-  else raycast_kernel<MODE, false><<<grid, kThreads, 0, stream>>>(P);
+  const size_t pad = smem_pad();
+  if (pad > 48 * 1024) {
+    (void)cudaFuncSetAttribute(raycast_kernel<MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pad);
+    (void)cudaFuncSetAttribute(raycast_kernel<MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pad);
+  }
+  if (P.has_aov) raycast_kernel<MODE, true><<<grid, kThreads, pad, stream>>>(P);
+  else raycast_kernel<MODE, false><<<grid, kThreads, pad, stream>>>(P);
   return cudaGetLastError();
 }
 
