@@ -359,10 +359,11 @@ def main():
             bytes_per_ray = st.primary_alg_bytes / st.primary_rays
             steps_per_ray = sum(st.primary_lookups) / st.primary_rays
             parity = bool(np.array_equal(ref_rgba, host_frame[0]))
-        traffic = None
+        traffic, warp_instr = None, None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):
-            traffic = json.load(open(tpath)).get(args.scene, {}).get("dram_bytes_per_launch")
+            prof = json.load(open(tpath)).get(args.scene, {})
+            traffic, warp_instr = prof.get("dram_bytes_per_launch"), prof.get("warp_instructions_per_launch")
         roof = None
         if bytes_per_ray is not None:
             achieved = bytes_per_ray * rays_per_frame / (ms_per_step * 1e-3) / 1e9  # per GPU: one launch = one frame
@@ -370,6 +371,13 @@ def main():
                     "traffic": traffic, "peak_source": peak_src, "kernel": "wx::raycast_kernel<0,false>",
                     "alg_bytes_per_ray": round(bytes_per_ray, 2), "lookups_per_ray": round(steps_per_ray, 2),
                     "rays_per_launch": rays_per_frame,
+                    # what actually binds the kernel: issue slots.  Warp instructions per launch are ncu's count
+                    # (profiles/traffic.json); the fraction is of 4 schedulers x 1 instruction per clock per SM at the
+                    # clock sampled during the run.
+                    "issue_slots": None if not (warp_instr and clocks and clocks.get("sm_mhz")) else {
+                        "warp_instructions_per_launch": warp_instr,
+                        "frac_of_peak": round(warp_instr / (torch.cuda.get_device_properties(0).multi_processor_count * 4 *
+                                                             clocks["sm_mhz"] * 1e6 * ms_per_step * 1e-3), 4)},
                     "note": "algorithmic bytes (SURVEY 8d) over the CUDA-event time of the kernel, L2 flushed before each launch; "
                             "the working set is L2-resident so this is a bandwidth-equivalent figure, the kernel is latency/issue bound"}
         out = {

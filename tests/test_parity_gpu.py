@@ -350,3 +350,53 @@ def test_persistent_work_queue_kernel_is_bit_identical():
                         "assets_all_modes or edge_cases or camera_batch_and_shards or synthetic_scenes or zero_directions"],
                        env=env, capture_output=True, text=True, timeout=1200)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+def test_randomized_scenes_and_cameras(gpu_ctx):
+    """Differential fuzz (seeded): random sparse trees incl. far-apart and out-of-world N5s, random cameras (inside
+    the volume, on integer coordinates, axis-aligned, outside the +-4096 world), every render mode -- bit-identical
+    frames and AOVs.  Exercises the exactness arguments of march_fast (floor trick at lattice planes, ties, nudges)."""
+    rng = np.random.default_rng(20240229)
+    from woxel_b200.render import make_desc
+    for case in range(12):
+        t = O.Tree()
+        n_blobs = int(rng.integers(1, 6))
+        for _ in range(n_blobs):
+            centre = rng.integers(-900, 900, 3) if rng.random() < 0.8 else rng.integers(-6000, 6000, 3)
+            ext = int(rng.integers(1, 40))
+            pts = centre + rng.integers(-ext, ext + 1, size=(int(rng.integers(1, 400)), 3))
+            t.set_voxels(pts.astype(np.int32))
+        if case % 3 == 0:  # a solid block: exact ties on flat faces
+            c0 = rng.integers(-100, 100, 3)
+            ax = [np.arange(c, c + int(rng.integers(2, 20))) for c in c0]
+            g = np.stack(np.meshgrid(*ax, indexing="ij"), -1).reshape(-1, 3)
+            t.set_voxels(g.astype(np.int32))
+        s = scenes.OracleScene(t)
+        tree = gpu_ctx.upload(make_desc(s.origins, s.kids5, s.vals5, s.tab5, s.kids4, s.vals4, s.tab4, s.vals3, s.tab3))
+        try:
+            for k in range(6):
+                kind = k % 6
+                if kind == 0:
+                    eye = tuple(rng.uniform(-1500, 1500, 3))
+                elif kind == 1:
+                    eye = tuple(float(v) for v in rng.integers(-300, 300, 3))  # exactly on lattice planes
+                elif kind == 2:
+                    eye = (float(rng.integers(-50, 50)) + 0.5, float(rng.integers(-50, 50)) + 0.5, -700.5)  # axis-aligned view
+                elif kind == 3:
+                    eye = tuple(rng.uniform(-4090, 4090, 3))
+                elif kind == 4:
+                    eye = tuple(rng.uniform(4000, 4300, 3))  # partly outside the world
+                else:
+                    eye = tuple(rng.uniform(-60, 60, 3))     # inside / next to the voxels
+                target = (eye[0], eye[1], eye[2] + 100.0) if kind == 2 else tuple(rng.uniform(-200, 200, 3))
+                mode = int(rng.integers(0, 5))
+                w, h = 64, 32
+                st = scenes.state_for(eye, target, w, h, mode=mode, show_grid=(1, 1, 1))
+                rgba, aov = gpu_ctx.render(tree, to_wx(st), w, h, aov=True)
+                ref, ref_aov, _ = s.gpu.render(st, w, h)
+                assert np.array_equal(rgba[0], ref), (case, k, eye, target, mode)
+                for name in ("state", "voxel", "leaf", "level", "iters", "mask"):
+                    assert np.array_equal(aov[name][0], ref_aov[name]), (case, k, name, eye, target, mode)
+                assert np.array_equal(_bits_nan_canonical(aov["pos"][0]), _bits_nan_canonical(ref_aov["pos"])), (case, k)
+        finally:
+            tree.free()
