@@ -71,10 +71,17 @@ __device__ __forceinline__ void render_pixel(const RenderParams& P, const PixelR
     }
     return;
   }
-  const WxState& s = (P.n_states == 1) ? P.s0 : P.states[q.cam];
+  // the ray basis: from the constant bank for a single state (the usual frame), else from the batch in global memory
+  V3 u, mv, wp, eye;
+  if (P.n_states == 1) {
+    u = V3{P.s0.u[0], P.s0.u[1], P.s0.u[2]}, mv = V3{P.s0.mv[0], P.s0.mv[1], P.s0.mv[2]};
+    wp = V3{P.s0.wp[0], P.s0.wp[1], P.s0.wp[2]}, eye = V3{P.s0.eye[0], P.s0.eye[1], P.s0.eye[2]};
+  } else {
+    const float4* s4 = reinterpret_cast<const float4*>(P.states + q.cam);  // eye, u, mv, wp are the float4s 8..11 of the state
+    const float4 e = __ldg(s4 + 8), a = __ldg(s4 + 9), b = __ldg(s4 + 10), c = __ldg(s4 + 11);
+    eye = V3{e.x, e.y, e.z}, u = V3{a.x, a.y, a.z}, mv = V3{b.x, b.y, b.z}, wp = V3{c.x, c.y, c.z};
+  }
   const float px = (float)q.x + 0.001f, py = (float)q.y + 0.001f;
-  const V3 u = V3{s.u[0], s.u[1], s.u[2]}, mv = V3{s.mv[0], s.mv[1], s.mv[2]}, wp = V3{s.wp[0], s.wp[1], s.wp[2]};
-  const V3 eye = V3{s.eye[0], s.eye[1], s.eye[2]};
   const V3 dir = normalize3((px * u + py * mv) + wp);
   shade_and_store<MODE, AOV>(P, q, hdda_ray(P.tree, eye, dir), dir);
 }
@@ -83,13 +90,17 @@ __device__ __forceinline__ void render_pixel(const RenderParams& P, const PixelR
 template <int MODE, bool AOV>
 __global__ void __launch_bounds__(kThreads, WX_MIN_BLOCKS) raycast_kernel(const __grid_constant__ RenderParams P) {
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t tx = blockIdx.x % P.tiles_x;
-  const uint32_t trow = blockIdx.x / P.tiles_x;                 // tile row among the rows this launch owns
-  const uint32_t band = (trow / P.tile_rows_per_band) * P.shard_count + P.shard_index;
+  const uint32_t tx = blockIdx.x;
+  const uint32_t trow = blockIdx.y;                             // tile row among the rows this launch owns
+  // band of this tile row and the row inside it; the two usual shapes (one band, or one tile row per band) need no division
+  uint32_t own_band = 0, in_band = trow;
+  if (P.tile_rows_per_band == 1u) own_band = trow, in_band = 0;
+  else if (P.own_bands > 1u) own_band = trow / P.tile_rows_per_band, in_band = trow - own_band * P.tile_rows_per_band;
+  const uint32_t band = own_band * P.shard_count + P.shard_index;
   PixelRef q;
   q.x = tx * kTileW + (warp & 1) * 8 + (lane & 7);
-  q.y = P.row_base + band * P.band_rows + (trow % P.tile_rows_per_band) * kTileH + (warp >> 1) * 4 + (lane >> 3);
-  q.cam = P.cam_base + blockIdx.y;
+  q.y = P.row_base + band * P.band_rows + in_band * kTileH + (warp >> 1) * 4 + (lane >> 3);
+  q.cam = P.cam_base + blockIdx.z;
   q.in_frame = q.x < P.width && q.y < P.row_end;
   q.dispatched = q.x < P.disp_w && q.y < P.disp_h;
   render_pixel<MODE, AOV>(P, q);
@@ -194,8 +205,8 @@ cudaError_t launch_raycast(RenderParams& P, uint32_t n_cams, uint32_t render_mod
   P.disp_w = (P.width / 8) * 8;
   P.disp_h = (P.height / 4) * 4;
   if (P.own_bands == 0 || n_cams == 0 || P.tiles_x == 0) return cudaSuccess;
-  const uint64_t blocks = (uint64_t)P.tiles_x * P.tile_rows_per_band * P.own_bands;
-  if (blocks > 0x7fffffffull || n_cams > 65535u) return cudaErrorInvalidConfiguration;
+  const uint64_t tile_rows = (uint64_t)P.tile_rows_per_band * P.own_bands;
+  if (P.tiles_x > 0x7fffffffu || tile_rows > 65535u || n_cams > 65535u) return cudaErrorInvalidConfiguration;
   if (work_counter && use_persistent()) {
     const uint64_t own_rows = (uint64_t)P.own_bands * P.band_rows;
     P.chunks_x = (P.width + 31u) / 32u;
@@ -218,7 +229,7 @@ cudaError_t launch_raycast(RenderParams& P, uint32_t n_cams, uint32_t render_mod
       }
     }
   }
-  dim3 grid((unsigned)blocks, n_cams, 1);
+  dim3 grid(P.tiles_x, (unsigned)tile_rows, n_cams);
   *launches = 1;
   switch (render_mode) {
     case 1: return launch_mode<1>(P, grid, stream);
