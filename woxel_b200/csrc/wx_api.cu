@@ -73,7 +73,7 @@ struct WxTree {
   WxContext* ctx = nullptr;
   std::vector<TreeOnDevice> on;  // one per context device
   std::vector<int4> origins;  // biased by kBias (wx_device.cuh)
-  int8_t root_grid[64];       // N5 index per 4096^3 cell of [-8192, 8192)^3, -1 = none (DevTree::root_grid)
+  int16_t root_grid[64];      // root cells of [-8192, 8192)^3 (DevTree::root_grid)
   uint32_t leaf_shift = 9;    // log2(bytes per leaf brick)
   bool fast_ok = true;        // every step size < 2^20: the fast march applies
   WxTreeInfo info{};
@@ -299,7 +299,8 @@ extern "C" int wx_tree_upload(WxContext* ctx, const WxTreeDesc* d, WxTree** out)
     return fail(ctx, WX_ERR_INVALID_ARGUMENT, "wx_tree_upload: missing array");
   if (d->n3 && d->tab3_elem_bytes != 1 && d->tab3_elem_bytes != 4)
     return fail(ctx, WX_ERR_INVALID_ARGUMENT, "wx_tree_upload: tab3_elem_bytes must be 1 or 4");
-  if (d->n4 >= kChildFlag || d->n3 >= kChildFlag) return fail(ctx, WX_ERR_UNSUPPORTED, "wx_tree_upload: too many nodes");
+  if (d->n5 > (uint32_t)kRootIndexMask || d->n4 >= kChildFlag || d->n3 >= kChildFlag)
+    return fail(ctx, WX_ERR_UNSUPPORTED, "wx_tree_upload: too many nodes");  // 16383 N5s would be 2 GB of N5 tables alone
 
   std::vector<uint32_t> e5, e4;
   std::vector<uint8_t> l3;
@@ -345,13 +346,14 @@ extern "C" int wx_tree_upload(WxContext* ctx, const WxTreeDesc* d, WxTree** out)
   for (uint32_t i = 0; i < d->n5; ++i)  // biased like the voxel coordinates the kernel derives from float bits (modular)
     t->origins[i] = make_int4((int)((uint32_t)d->origins[3 * i] + kBias), (int)((uint32_t)d->origins[3 * i + 1] + kBias),
                               (int)((uint32_t)d->origins[3 * i + 2] + kBias), 0);
-  memset(t->root_grid, 0xff, sizeof(t->root_grid));
+  for (int16_t& v : t->root_grid) v = (int16_t)kRootNone;
   for (uint32_t i = d->n5; i-- > 0;) {  // descending: the first of equal origins wins, as in the reference's scan
     const int32_t* o = d->origins + 3 * i;
     const int64_t cx = ((int64_t)o[0] >> 12) + 2, cy = ((int64_t)o[1] >> 12) + 2, cz = ((int64_t)o[2] >> 12) + 2;
     if ((o[0] & 4095) || (o[1] & 4095) || (o[2] & 4095)) continue;  // an unaligned origin never equals (pos >> 12) << 12
     if (cx < 0 || cx > 3 || cy < 0 || cy > 3 || cz < 0 || cz > 3) continue;
-    t->root_grid[cx * 16 + cy * 4 + cz] = i < 127 ? (int8_t)i : (int8_t)-2;
+    const bool beyond = cx < 1 || cx > 2 || cy < 1 || cy > 2 || cz < 1 || cz > 2;  // origin component outside [-4096, 0]
+    t->root_grid[cx * 16 + cy * 4 + cz] = i <= (uint32_t)kRootIndexMask ? (int16_t)(i | (beyond ? kRootBeyond : 0)) : (int16_t)kRootScan;
   }
   t->leaf_shift = leaf_shift;
   // the fast march needs byte leaves and every step size below 2^20 (wx_device.cuh); anything else takes the exact march

@@ -46,6 +46,7 @@ constexpr float kMagic = 12582912.0f;        // 1.5 * 2^23
 constexpr uint32_t kChildFlag = 0x80000000u;
 constexpr uint32_t kNoCache = 0x80000000u;   // cursor.dbits: nothing cached, every lookup starts at the root
 constexpr float kFastMaxSize = 1048576.0f;   // 2^20: largest step size the fast march accepts
+constexpr int kRootNone = -1, kRootScan = -2, kRootBeyond = 0x4000, kRootIndexMask = 0x3fff;
 
 struct DevTree {
   const uint32_t* __restrict__ e5;
@@ -58,10 +59,11 @@ struct DevTree {
   uint32_t n5, n4, n3;
   uint32_t leaf_shift;                 // log2(bytes per leaf): 9 (u8 voxels) or 11 (u32 voxels)
   uint32_t fast_ok;                    // every tile/leaf size < kFastMaxSize
-  // N5 index (or -1) of the 4x4x4 root cells covering [-8192, 8192)^3, cell = ((x>>12)+2)*16 + ((y>>12)+2)*4 + (z>>12)+2:
-  // everything a ray can reach from inside the +-4096 world with one level-0 step.  Beyond it, or where the
-  // cell holds -2 (index does not fit a byte): scan origins.
-  int8_t root_grid[64];
+  // The 4x4x4 root cells covering [-8192, 8192)^3, cell = ((x>>12)+2)*16 + ((y>>12)+2)*4 + (z>>12)+2: everything a ray
+  // can reach from inside the +-4096 world with one level-0 step.  Entry: kRootNone (no N5 there), kRootScan (index does
+  // not fit: scan origins), else the N5 index, | kRootBeyond when the cell reaches outside the world (its origin has a
+  // component outside [-4096, 0]), where the march must test the bounds.  Outside the grid: scan origins.
+  int16_t root_grid[64];
 };
 
 struct AovPtrs {
@@ -268,19 +270,21 @@ static __device__ __noinline__ int scan_roots(const DevTree& T, uint32_t x, uint
   }
   return -1;
 }
+// The N5 at (pos >> 12) << 12 contains positions outside the +-4096 world (origin component not in [-4096, 0]).
+__device__ __forceinline__ bool reaches_beyond(uint32_t x, uint32_t y, uint32_t z) {
+  const uint32_t span = 4096u;  // biased origin - (kBias - 4096) must be 0 or 4096
+  return ((x & ~4095u) - (kBias - 4096u)) > span || ((y & ~4095u) - (kBias - 4096u)) > span || ((z & ~4095u) - (kBias - 4096u)) > span;
+}
+// Root entry for the N5 cell of (x, y, z): kRootNone, or the N5 index with kRootBeyond or-ed in.
 __device__ __forceinline__ int find_root(const DevTree& T, uint32_t x, uint32_t y, uint32_t z) {
   const uint32_t c0 = (kBias >> 12) - 2u;
   const uint32_t cx = (x >> 12) - c0, cy = (y >> 12) - c0, cz = (z >> 12) - c0;
   if ((cx | cy | cz) < 4u) {
     const int v = (int)T.root_grid[cx * 16u + cy * 4u + cz];
-    if (v != -2) return v;
+    if (v != kRootScan) return v;
   }
-  return scan_roots(T, x, y, z);
-}
-// The N5 at (pos >> 12) << 12 contains positions outside the +-4096 world (origin component not in [-4096, 0]).
-__device__ __forceinline__ bool reaches_beyond(uint32_t x, uint32_t y, uint32_t z) {
-  const uint32_t span = 4096u;  // biased origin - (kBias - 4096) must be 0 or 4096
-  return ((x & ~4095u) - (kBias - 4096u)) > span || ((y & ~4095u) - (kBias - 4096u)) > span || ((z & ~4095u) - (kBias - 4096u)) > span;
+  const int n5 = scan_roots(T, x, y, z);
+  return n5 < 0 ? kRootNone : (n5 | (reaches_beyond(x, y, z) ? kRootBeyond : 0));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -316,14 +320,14 @@ __device__ __forceinline__ bool out_of_bounds(float x, float y, float z) {
 // `beyond`: the bounds test of :100-103 can succeed at this position (it cannot inside an N5 whose
 // origin lies in [-4096, 0]^3).
 __device__ __forceinline__ bool enter_root(const DevTree& T, Cursor& c, uint32_t& dv, uint32_t x, uint32_t y, uint32_t z) {
-  const int n5 = find_root(T, x, y, z);
-  if (n5 < 0) {
+  const int r = find_root(T, x, y, z);
+  if (r < 0) {
     c.dbits = kNoCache;
     return true;
   }
-  c.q5 = T.e5 + (size_t)n5 * 32768u;
+  c.q5 = T.e5 + (size_t)(r & ~kRootBeyond) * 32768u;
   dv = 128u;
-  return reaches_beyond(x, y, z);
+  return (r & kRootBeyond) != 0;
 }
 
 // One lookup L(pos) through the cursor, for the exact march (bounds tested every step).
