@@ -139,6 +139,7 @@ __device__ __forceinline__ f32x2 pk(float lo, float hi) {
 __device__ __forceinline__ f32x2 bc(float v) { return pk(v, v); }
 __device__ __forceinline__ float lo(f32x2 v) { return __uint_as_float((uint32_t)v); }
 __device__ __forceinline__ float hi(f32x2 v) { return __uint_as_float((uint32_t)(v >> 32)); }
+#ifndef WX_NO_F32X2
 __device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
   f32x2 d;
   asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
@@ -164,6 +165,13 @@ __device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {  // never feed this to
   asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
   return d;
 }
+#else  // A/B variant: the same operations as scalar instructions (more issue slots, more independent work per stage)
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { return pk(__fadd_rn(lo(a), lo(b)), __fadd_rn(hi(a), hi(b))); }
+__device__ __forceinline__ f32x2 add2_rd(f32x2 a, f32x2 b) { return pk(__fadd_rd(lo(a), lo(b)), __fadd_rd(hi(a), hi(b))); }
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) { return pk(__fsub_rn(lo(a), lo(b)), __fsub_rn(hi(a), hi(b))); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { return pk(__fmaf_rn(lo(a), lo(b), lo(c)), __fmaf_rn(hi(a), hi(b), hi(c))); }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { return pk(__fmul_rn(lo(a), lo(b)), __fmul_rn(hi(a), hi(b))); }
+#endif
 __device__ __forceinline__ float rcp_approx(float v) {  // MUFU.RCP, <= 1 ulp
   float r;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
