@@ -400,3 +400,23 @@ def test_randomized_scenes_and_cameras(gpu_ctx):
                 assert np.array_equal(_bits_nan_canonical(aov["pos"][0]), _bits_nan_canonical(ref_aov["pos"])), (case, k)
         finally:
             tree.free()
+
+
+def test_large_camera_batch_mixed_modes(gpu_ctx):
+    """130 states: the pipelined read-back groups cameras 3 per chunk, with render-mode changes inside a chunk and a
+    partial last chunk; every frame equals its single-frame render."""
+    name, w, h = "small_sphere", 64, 32
+    tree = gpu_tree(gpu_ctx, name)
+    rng = np.random.default_rng(9)
+    states = []
+    for k in range(130):
+        th = 2 * np.pi * k / 130
+        eye = (0.5 + 170 * np.sin(th), 20.5 + 0.1 * k, 0.5 - 170 * np.cos(th))
+        states.append(to_wx(scenes.state_for(eye, (0.5, 0.5, 0.5), w, h, mode=int(rng.integers(0, 5)))))
+    batch, _ = gpu_ctx.render(tree, states, w, h)
+    assert gpu_ctx.last_render_info().launches >= 44  # 44 chunks, more where the mode changes inside one
+    for k in (0, 1, 2, 3, 64, 65, 127, 128, 129):
+        single, _ = gpu_ctx.render(tree, states[k], w, h)
+        assert np.array_equal(batch[k], single[0]), k
+    ref, _, _ = scenes.get_scene(name).gpu.render(scenes.state_for((0.5, 20.5, -169.5), (0.5, 0.5, 0.5), w, h, mode=int(states[0].render_mode[0])), w, h, aov=False)
+    assert np.array_equal(batch[0], ref)
