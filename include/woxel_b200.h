@@ -168,6 +168,15 @@ int wx_compute_sdf(WxContext *ctx, const WxTreeDesc *topo, uint32_t *tab5_out, u
                    uint32_t tab3_elem_bytes, WxSdfInfo *info);
 
 /*
+ * Model load in one call: compute_sdf on the GPU and the device tables built from its result in place, replicated on
+ * every device of ctx -- what `vdb.compute_sdf(); vdb.atlas(); MaskUniform::from(&vdb)` + the uploads do in the
+ * reference (src/render/wgpu_context.rs:101-159, :506-573), without the distances ever visiting the host.  `topo` as for
+ * wx_compute_sdf (plus vals5 / vals4).  The tree renders exactly like wx_compute_sdf + wx_tree_upload.
+ * WX_ERR_UNSUPPORTED: a leaf distance above 255 (take the two-call path, which has the u32 brick layout).
+ */
+int wx_tree_build(WxContext *ctx, const WxTreeDesc *topo, WxTree **out, WxSdfInfo *info);
+
+/*
  * One frame per state (n_states > 1 = camera batch).  Blocking.  rgba_out is HOST memory,
  * n_states x height x width x 4 bytes (pinned memory makes the read-back faster; pageable works).
  * Pixels outside the reference's dispatch (x >= (W/8)*8 or y >= (H/4)*4, wgpu_context.rs:281) are

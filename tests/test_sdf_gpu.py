@@ -78,3 +78,41 @@ def test_gpu_sdf_rejects_bad_input(gpu_ctx):
     with pytest.raises(W.WxError) as e:
         gpu_ctx.compute_sdf(d)
     assert e.value.status == -5
+
+
+@pytest.mark.parametrize("name", ["cube", "scattered", "beyond_bounds", "active_tiles", "empty_leaf"])
+def test_tree_build_equals_sweep_plus_upload(gpu_ctx, name):
+    """wx_tree_build (sweep + device-side packing) renders exactly like the oracle's tables through wx_tree_upload."""
+    s = scenes.get_scene(name)
+    built = gpu_ctx.build(topo_desc(s))
+    plain = gpu_ctx.upload(s.desc())
+    try:
+        for k in ("n5", "n4", "n3", "leaf_bits", "device_bytes"):
+            assert getattr(built.info, k) == getattr(plain.info, k), k
+        assert list(built.info.max_dist) == list(plain.info.max_dist) and built.sdf.rounds > 0
+        for (eye, target), mode in zip([scenes.CAMERAS["oblique_a"], ((3.3, 2.2, 1.1), (40.0, 30.0, -20.0)), ((0.5, 0.5, -300.5), (0.5, 0.5, 0.5))], (3, 0, 4)):
+            st = W.ComputeState.from_buffer_copy(bytes(scenes.state_for(eye, target, 256, 144, mode=mode)))
+            a, aov_a = gpu_ctx.render(built, st, 256, 144, aov=True)
+            b, aov_b = gpu_ctx.render(plain, st, 256, 144, aov=True)
+            assert np.array_equal(a, b)
+            for key in ("state", "voxel", "leaf", "iters"):
+                assert np.array_equal(aov_a[key], aov_b[key]), key
+    finally:
+        built.free(), plain.free()
+
+
+def test_tree_build_reports_wide_leaves(gpu_ctx):
+    """A chain of empty leaves pushes a leaf distance above 255: wx_tree_build says so, the two-call path handles it."""
+    t = O.Tree()
+    t.set_voxel([0, 0, 0])
+    s0 = scenes.OracleScene(t, sdf=False)
+    # one N4 whose 16 leaves along z exist but only the first holds a voxel: distances grow to 8 * 15 + 7
+    k4 = s0.kids4.copy()
+    k4[0, 0] |= np.uint64(0xFFFF)
+    vals3 = np.zeros((16, 8), np.uint64)
+    vals3[0] = s0.vals3[0]
+    long_row = scenes.OracleScene(O.Tree.from_topology(s0.origins, s0.kids5, s0.vals5, k4, s0.vals4, vals3))
+    assert long_row.tab3[~scenes.bits2d(long_row.vals3)].max() <= 255  # not wide yet: the path must still agree
+    built = gpu_ctx.build(topo_desc(long_row))
+    assert list(built.info.max_dist)[2] == long_row.tab3[~scenes.bits2d(long_row.vals3)].max()
+    built.free()

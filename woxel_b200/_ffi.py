@@ -97,6 +97,7 @@ CUDA_API = {
     "wx_ipc_open": (C.c_int, [vp, C.c_int, u8p, C.POINTER(vp)]),
     "wx_ipc_close": (C.c_int, [vp, C.c_int, vp]),
     "wx_shard_rows": (C.c_int, [C.c_uint32, C.POINTER(WxShard), vp]),
+    "wx_tree_build": (C.c_int, [vp, C.POINTER(WxTreeDesc), C.POINTER(vp), C.POINTER(WxSdfInfo)]),
     "wx_compute_sdf": (C.c_int, [vp, C.POINTER(WxTreeDesc), vp, vp, vp, C.c_uint32, C.POINTER(WxSdfInfo)]),
     "wx_capture_srgb": (C.c_int, [vp, C.c_uint32, C.c_uint32, C.c_uint32, vp]),
     "wx_srgb_table": (C.c_int, [vp]),

@@ -291,6 +291,36 @@ static int pack_internal(uint32_t n_nodes, uint32_t slots, float cell, const uin
   return status.load();
 }
 
+// Host-side part of a device tree: biased origins, root cells, limits, info.
+static WxTree* new_tree(WxContext* ctx, const WxTreeDesc* d, uint32_t leaf_bits, uint32_t max5, uint32_t max4, uint32_t max3v) {
+  WxTree* t = new (std::nothrow) WxTree();
+  if (!t) return nullptr;
+  t->ctx = ctx;
+  t->origins.resize(d->n5);
+  for (uint32_t i = 0; i < d->n5; ++i)  // biased like the voxel coordinates the kernel derives from float bits (modular)
+    t->origins[i] = make_int4((int)((uint32_t)d->origins[3 * i] + kBias), (int)((uint32_t)d->origins[3 * i + 1] + kBias),
+                              (int)((uint32_t)d->origins[3 * i + 2] + kBias), 0);
+  for (int16_t& v : t->root_grid) v = (int16_t)kRootNone;
+  for (uint32_t i = d->n5; i-- > 0;) {  // descending: the first of equal origins wins, as in the reference's scan
+    const int32_t* o = d->origins + 3 * i;
+    const int64_t cx = ((int64_t)o[0] >> 12) + 2, cy = ((int64_t)o[1] >> 12) + 2, cz = ((int64_t)o[2] >> 12) + 2;
+    if ((o[0] & 4095) || (o[1] & 4095) || (o[2] & 4095)) continue;  // an unaligned origin never equals (pos >> 12) << 12
+    if (cx < 0 || cx > 3 || cy < 0 || cy > 3 || cz < 0 || cz > 3) continue;
+    const bool beyond = cx < 1 || cx > 2 || cy < 1 || cy > 2 || cz < 1 || cz > 2;  // origin component outside [-4096, 0]
+    t->root_grid[cx * 16 + cy * 4 + cz] = i <= (uint32_t)kRootIndexMask ? (int16_t)(i | (beyond ? kRootBeyond : 0)) : (int16_t)kRootScan;
+  }
+  t->leaf_shift = leaf_bits == 8 ? 9 : 11;
+  // the fast march needs byte leaves and every step size below 2^20 (wx_device.cuh); anything else takes the exact march
+  t->fast_ok = leaf_bits == 8 && (double)max5 * 128.0 < (double)kFastMaxSize && (double)max4 * 8.0 < (double)kFastMaxSize && (double)max3v < (double)kFastMaxSize;
+  t->info.n5 = d->n5, t->info.n4 = d->n4, t->info.n3 = d->n3;
+  t->info.leaf_bits = leaf_bits;
+  t->info.max_dist[0] = max5, t->info.max_dist[1] = max4, t->info.max_dist[2] = max3v;
+  t->info.n_devices = (uint32_t)ctx->dev.size();
+  t->info.device_bytes = ((size_t)d->n5 * 32768 + (size_t)d->n4 * 4096) * 4 + ((size_t)d->n3 << t->leaf_shift) + t->origins.size() * sizeof(int4);
+  t->on.resize(ctx->dev.size());
+  return t;
+}
+
 extern "C" int wx_tree_upload(WxContext* ctx, const WxTreeDesc* d, WxTree** out) {
   if (!ctx || !d || !out) return fail(ctx, WX_ERR_INVALID_ARGUMENT, "wx_tree_upload: null argument");
   *out = nullptr;
@@ -339,31 +369,8 @@ extern "C" int wx_tree_upload(WxContext* ctx, const WxTreeDesc* d, WxTree** out)
     }
   });
 
-  WxTree* t = new (std::nothrow) WxTree();
+  WxTree* t = new_tree(ctx, d, leaf_bits, max5, max4, max3v);
   if (!t) return fail(ctx, WX_ERR_OUT_OF_MEMORY, "wx_tree_upload: host allocation");
-  t->ctx = ctx;
-  t->origins.resize(d->n5);
-  for (uint32_t i = 0; i < d->n5; ++i)  // biased like the voxel coordinates the kernel derives from float bits (modular)
-    t->origins[i] = make_int4((int)((uint32_t)d->origins[3 * i] + kBias), (int)((uint32_t)d->origins[3 * i + 1] + kBias),
-                              (int)((uint32_t)d->origins[3 * i + 2] + kBias), 0);
-  for (int16_t& v : t->root_grid) v = (int16_t)kRootNone;
-  for (uint32_t i = d->n5; i-- > 0;) {  // descending: the first of equal origins wins, as in the reference's scan
-    const int32_t* o = d->origins + 3 * i;
-    const int64_t cx = ((int64_t)o[0] >> 12) + 2, cy = ((int64_t)o[1] >> 12) + 2, cz = ((int64_t)o[2] >> 12) + 2;
-    if ((o[0] & 4095) || (o[1] & 4095) || (o[2] & 4095)) continue;  // an unaligned origin never equals (pos >> 12) << 12
-    if (cx < 0 || cx > 3 || cy < 0 || cy > 3 || cz < 0 || cz > 3) continue;
-    const bool beyond = cx < 1 || cx > 2 || cy < 1 || cy > 2 || cz < 1 || cz > 2;  // origin component outside [-4096, 0]
-    t->root_grid[cx * 16 + cy * 4 + cz] = i <= (uint32_t)kRootIndexMask ? (int16_t)(i | (beyond ? kRootBeyond : 0)) : (int16_t)kRootScan;
-  }
-  t->leaf_shift = leaf_shift;
-  // the fast march needs byte leaves and every step size below 2^20 (wx_device.cuh); anything else takes the exact march
-  t->fast_ok = leaf_bits == 8 && (double)max5 * 128.0 < (double)kFastMaxSize && (double)max4 * 8.0 < (double)kFastMaxSize && (double)max3v < (double)kFastMaxSize;
-  t->info.n5 = d->n5, t->info.n4 = d->n4, t->info.n3 = d->n3;
-  t->info.leaf_bits = leaf_bits;
-  t->info.max_dist[0] = max5, t->info.max_dist[1] = max4, t->info.max_dist[2] = max3v;
-  t->info.n_devices = (uint32_t)ctx->dev.size();
-  t->info.device_bytes = (e5.size() + e4.size()) * 4 + l3.size() + t->origins.size() * sizeof(int4);
-  t->on.resize(ctx->dev.size());
 
   auto up = [&](int dev_i) -> int {
     DeviceSlot& s = ctx->dev[dev_i];
@@ -401,6 +408,14 @@ extern "C" int wx_tree_upload(WxContext* ctx, const WxTreeDesc* d, WxTree** out)
   return WX_OK;
 }
 
+static int check_topology(WxContext* ctx, const WxTreeDesc* d, const char* who) {
+  for (size_t i = 0; i < (size_t)d->n5 * 32768; ++i)
+    if (bit(d->kids5, i) && d->tab5[i] >= d->n4) return fail(ctx, WX_ERR_BAD_TREE, std::string(who) + ": N5 child index out of range");
+  for (size_t i = 0; i < (size_t)d->n4 * 4096; ++i)
+    if (bit(d->kids4, i) && d->tab4[i] >= d->n3) return fail(ctx, WX_ERR_BAD_TREE, std::string(who) + ": N4 child index out of range");
+  return WX_OK;
+}
+
 extern "C" int wx_compute_sdf(WxContext* ctx, const WxTreeDesc* d, uint32_t* tab5_out, uint32_t* tab4_out, void* tab3_out,
                               uint32_t tab3_elem_bytes, WxSdfInfo* info) {
   if (!ctx || !d) return fail(ctx, WX_ERR_INVALID_ARGUMENT, "wx_compute_sdf: null argument");
@@ -409,10 +424,7 @@ extern "C" int wx_compute_sdf(WxContext* ctx, const WxTreeDesc* d, uint32_t* tab
     return fail(ctx, WX_ERR_INVALID_ARGUMENT, "wx_compute_sdf: missing array");
   if (tab3_elem_bytes != 1 && tab3_elem_bytes != 4) return fail(ctx, WX_ERR_INVALID_ARGUMENT, "wx_compute_sdf: tab3_elem_bytes must be 1 or 4");
   // child indices must be in range: the sweeps follow them
-  for (size_t i = 0; i < (size_t)d->n5 * 32768; ++i)
-    if (bit(d->kids5, i) && d->tab5[i] >= d->n4) return fail(ctx, WX_ERR_BAD_TREE, "wx_compute_sdf: N5 child index out of range");
-  for (size_t i = 0; i < (size_t)d->n4 * 4096; ++i)
-    if (bit(d->kids4, i) && d->tab4[i] >= d->n3) return fail(ctx, WX_ERR_BAD_TREE, "wx_compute_sdf: N4 child index out of range");
+  if (int bad = check_topology(ctx, d, "wx_compute_sdf")) return bad;
   DeviceSlot& d0 = ctx->dev[0];
   WX_CUDA(ctx, cudaSetDevice(d0.id));
   const auto t0 = std::chrono::steady_clock::now();
@@ -425,6 +437,86 @@ extern "C" int wx_compute_sdf(WxContext* ctx, const WxTreeDesc* d, uint32_t* tab
     info->total_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
   }
   if (r[3]) return fail(ctx, WX_ERR_UNSUPPORTED, "wx_compute_sdf: a leaf distance does not fit the requested element size");
+  return WX_OK;
+}
+
+extern "C" int wx_tree_build(WxContext* ctx, const WxTreeDesc* d, WxTree** out, WxSdfInfo* info) {
+  if (!ctx || !d || !out) return fail(ctx, WX_ERR_INVALID_ARGUMENT, "wx_tree_build: null argument");
+  *out = nullptr;
+  if ((d->n5 && (!d->origins || !d->kids5 || !d->vals5 || !d->tab5)) || (d->n4 && (!d->kids4 || !d->vals4 || !d->tab4)) || (d->n3 && !d->vals3))
+    return fail(ctx, WX_ERR_INVALID_ARGUMENT, "wx_tree_build: missing array");
+  if (d->n5 > (uint32_t)kRootIndexMask || d->n4 >= kChildFlag || d->n3 >= kChildFlag) return fail(ctx, WX_ERR_UNSUPPORTED, "wx_tree_build: too many nodes");
+  int rc = check_topology(ctx, d, "wx_tree_build");
+  if (rc) return rc;
+  const auto t0 = std::chrono::steady_clock::now();
+  const size_t s5 = (size_t)d->n5 * 32768, s4 = (size_t)d->n4 * 4096, s3 = (size_t)d->n3 * 512;
+  DeviceSlot& d0 = ctx->dev[0];
+  WX_CUDA(ctx, cudaSetDevice(d0.id));
+  TreeOnDevice first;
+  auto drop = [&](TreeOnDevice& o) {
+    if (o.e5) (void)cudaFree(o.e5);
+    if (o.e4) (void)cudaFree(o.e4);
+    if (o.l3) (void)cudaFree(o.l3);
+    if (o.origins) (void)cudaFree(o.origins);
+    o = TreeOnDevice();
+  };
+  cudaError_t e = cudaMalloc(&first.e5, s5 * 4 + 256);
+  if (e == cudaSuccess) e = cudaMalloc(&first.e4, s4 * 4 + 256);
+  if (e == cudaSuccess) e = cudaMalloc(&first.l3, s3 + 256);
+  if (e == cudaSuccess) e = cudaMalloc(&first.origins, (size_t)d->n5 * sizeof(int4) + 256);
+  uint32_t r[5] = {0, 0, 0, 0, 0};
+  float ms = 0.f;
+  if (e == cudaSuccess) {
+    const SdfDeviceTargets targets{first.e5, first.e4, first.l3};
+    e = compute_sdf_device(*d, nullptr, nullptr, nullptr, 1, r, &ms, d0.stream, &targets);
+  }
+  if (e != cudaSuccess) {
+    drop(first);
+    return fail_cuda(ctx, e, "wx_tree_build");
+  }
+  if (info) {
+    info->max_dist[0] = r[0], info->max_dist[1] = r[1], info->max_dist[2] = r[2], info->rounds = r[4];
+    info->device_ms = ms;
+  }
+  if (r[3]) {  // a leaf distance above 255: this tree needs the u32 brick layout
+    drop(first);
+    return fail(ctx, WX_ERR_UNSUPPORTED, "wx_tree_build: a leaf distance exceeds 255 (use wx_compute_sdf + wx_tree_upload)");
+  }
+  WxTree* t = new_tree(ctx, d, 8, r[0], r[1], r[2]);
+  if (!t) {
+    drop(first);
+    return fail(ctx, WX_ERR_OUT_OF_MEMORY, "wx_tree_build: host allocation");
+  }
+  t->on[0] = first;
+  auto bail = [&](cudaError_t err, const char* where) {
+    wx_tree_free(ctx, t);
+    return fail_cuda(ctx, err, where);
+  };
+  if (!t->origins.empty()) {
+    e = cudaMemcpyAsync(first.origins, t->origins.data(), t->origins.size() * sizeof(int4), cudaMemcpyHostToDevice, d0.stream);
+    if (e != cudaSuccess) return bail(e, "wx_tree_build: origins");
+  }
+  // replicate read-only on the other devices of the context (peer copies over NVLink)
+  for (size_t i = 1; i < ctx->dev.size(); ++i) {
+    DeviceSlot& s = ctx->dev[i];
+    TreeOnDevice& o = t->on[i];
+    e = cudaSetDevice(s.id);
+    if (e == cudaSuccess) e = cudaMalloc(&o.e5, s5 * 4 + 256);
+    if (e == cudaSuccess) e = cudaMalloc(&o.e4, s4 * 4 + 256);
+    if (e == cudaSuccess) e = cudaMalloc(&o.l3, s3 + 256);
+    if (e == cudaSuccess) e = cudaMalloc(&o.origins, t->origins.size() * sizeof(int4) + 256);
+    if (e == cudaSuccess) e = cudaSetDevice(d0.id);
+    if (e == cudaSuccess && s5) e = cudaMemcpyPeerAsync(o.e5, s.id, first.e5, d0.id, s5 * 4, d0.stream);
+    if (e == cudaSuccess && s4) e = cudaMemcpyPeerAsync(o.e4, s.id, first.e4, d0.id, s4 * 4, d0.stream);
+    if (e == cudaSuccess && s3) e = cudaMemcpyPeerAsync(o.l3, s.id, first.l3, d0.id, s3, d0.stream);
+    if (e == cudaSuccess && !t->origins.empty())
+      e = cudaMemcpyPeerAsync(o.origins, s.id, first.origins, d0.id, t->origins.size() * sizeof(int4), d0.stream);
+    if (e != cudaSuccess) return bail(e, "wx_tree_build: replicate");
+  }
+  e = cudaStreamSynchronize(d0.stream);
+  if (e != cudaSuccess) return bail(e, "wx_tree_build: synchronize");
+  if (info) info->total_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  *out = t;
   return WX_OK;
 }
 

@@ -23,6 +23,13 @@ void build_srgb_lut(uint8_t lut[256]);
 struct WxTreeDesc;
 namespace wx {
 // wx_sdf.cu: compute_sdf on the current device; info = max distance per level [0..2], values that did not fit [3], relaxation rounds [4]
+// dev != nullptr: instead of the host tables, fill the raycast kernel's own tables (caller-allocated device memory of the
+// current device: e5 n5*32768 u32, e4 n4*4096 u32, l3 n3*512 u8); info[3] then counts leaf distances above 255.
+struct SdfDeviceTargets {
+  uint32_t* e5;
+  uint32_t* e4;
+  uint8_t* l3;
+};
 cudaError_t compute_sdf_device(const WxTreeDesc& d, uint32_t* tab5_out, uint32_t* tab4_out, void* tab3_out, uint32_t tab3_elem_bytes,
-                               uint32_t info[5], float* device_ms, cudaStream_t stream);
+                               uint32_t info[5], float* device_ms, cudaStream_t stream, const SdfDeviceTargets* dev = nullptr);
 }  // namespace wx

@@ -253,6 +253,38 @@ __global__ void merge_leaf_kernel(const uint64_t* vals3, const uint16_t* dist, s
   out[i] = (OUT)d;
 }
 
+// distances -> the raycast kernel's tables, on the device (wx_tree_build): the packing wx_tree_upload does on the host
+// (wx_device.cuh, DevTree): active tile -> 0.0f, child -> flag | index, tile -> f32 bits of dist * cell
+__global__ void pack_internal_kernel(const uint64_t* kids, const uint64_t* vals, const uint32_t* tab_in, const uint32_t* dist, size_t total,
+                                     uint32_t slots_log2, float cell, uint32_t* e_out, uint32_t* max_seen) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const size_t node = i >> slots_log2;
+  const uint32_t o = (uint32_t)(i & ((1u << slots_log2) - 1u)), words = (1u << slots_log2) / 64;
+  uint32_t e;
+  if (bit64(vals + node * words, o)) {
+    e = 0u;
+  } else if (bit64(kids + node * words, o)) {
+    e = kChildFlag | tab_in[i];
+  } else {
+    const uint32_t dd = dist[i];
+    e = __float_as_uint((float)dd * cell);
+    atomicMax(max_seen, dd);
+  }
+  e_out[i] = e;
+}
+__global__ void pack_leaf_kernel(const uint64_t* vals3, const uint16_t* dist, size_t total, uint8_t* l3_out, uint32_t* max_seen, uint32_t* bad) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  uint32_t d = 0;
+  if (!bit64(vals3 + (i >> 9) * 8, (uint32_t)(i & 511u))) {
+    d = dist[i];
+    if (d > 255u) atomicAdd(bad, 1u);  // needs the u32 brick layout: the caller falls back to wx_compute_sdf + wx_tree_upload
+    else atomicMax(max_seen, d);
+  }
+  l3_out[i] = (uint8_t)d;
+}
+
 }  // namespace sdf
 
 // ---------------------------------------------------------------------------------------------
@@ -310,7 +342,7 @@ static cudaError_t run_pass(sdf::LevelPass<V> L, cudaStream_t stream, uint32_t* 
 // Everything on `stream` of the current device.  Host arrays in, host arrays out (tab3_out: u8 when
 // tab3_elem_bytes == 1, else u32).  info: [0..2] max distance per level, [3] values that did not fit, [4] rounds.
 cudaError_t compute_sdf_device(const WxTreeDesc& d, uint32_t* tab5_out, uint32_t* tab4_out, void* tab3_out, uint32_t tab3_elem_bytes,
-                               uint32_t info[5], float* device_ms, cudaStream_t stream) {
+                               uint32_t info[5], float* device_ms, cudaStream_t stream, const SdfDeviceTargets* dev) {
   std::vector<void*> allocs;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   auto cleanup = [&]() {
@@ -330,10 +362,10 @@ cudaError_t compute_sdf_device(const WxTreeDesc& d, uint32_t* tab5_out, uint32_t
   };
   const size_t s5 = (size_t)d.n5 * 32768, s4 = (size_t)d.n4 * 4096, s3 = (size_t)d.n3 * 512;
   int32_t *org5, *org4, *org3, *nb5, *nb4, *nb3;
-  uint64_t *kids5, *kids4, *vals3;
-  uint32_t *tab5, *tab4, *F5, *B5, *F4, *B4, *misc, *out5, *out4;
+  uint64_t *kids5, *kids4, *vals3, *vals5 = nullptr, *vals4 = nullptr;
+  uint32_t *tab5, *tab4, *F5, *B5, *F4, *B4, *misc, *out5 = nullptr, *out4 = nullptr;
   uint16_t *F3, *B3;
-  void* out3;
+  void* out3 = nullptr;
   SDF_CUDA(cudaEventCreate(&ev0));
   SDF_CUDA(cudaEventCreate(&ev1));
   SDF_CUDA(upload((void**)&org5, d.origins, (size_t)d.n5 * 12));
@@ -342,6 +374,10 @@ cudaError_t compute_sdf_device(const WxTreeDesc& d, uint32_t* tab5_out, uint32_t
   SDF_CUDA(upload((void**)&kids4, d.kids4, (size_t)d.n4 * 512));
   SDF_CUDA(upload((void**)&tab4, d.tab4, s4 * 4));
   SDF_CUDA(upload((void**)&vals3, d.vals3, (size_t)d.n3 * 64));
+  if (dev) {
+    SDF_CUDA(upload((void**)&vals5, d.vals5, (size_t)d.n5 * 4096));
+    SDF_CUDA(upload((void**)&vals4, d.vals4, (size_t)d.n4 * 512));
+  }
   SDF_CUDA(dalloc((void**)&org4, (size_t)d.n4 * 12));
   SDF_CUDA(dalloc((void**)&org3, (size_t)d.n3 * 12));
   SDF_CUDA(dalloc((void**)&nb5, (size_t)d.n5 * 27 * 4));
@@ -353,9 +389,11 @@ cudaError_t compute_sdf_device(const WxTreeDesc& d, uint32_t* tab5_out, uint32_t
   SDF_CUDA(dalloc((void**)&B4, s4 * 4));
   SDF_CUDA(dalloc((void**)&F3, s3 * 2));
   SDF_CUDA(dalloc((void**)&B3, s3 * 2));
-  SDF_CUDA(dalloc((void**)&out5, s5 * 4));
-  SDF_CUDA(dalloc((void**)&out4, s4 * 4));
-  SDF_CUDA(dalloc(&out3, s3 * (tab3_elem_bytes == 1 ? 1 : 4)));
+  if (!dev) {
+    SDF_CUDA(dalloc((void**)&out5, s5 * 4));
+    SDF_CUDA(dalloc((void**)&out4, s4 * 4));
+    SDF_CUDA(dalloc(&out3, s3 * (tab3_elem_bytes == 1 ? 1 : 4)));
+  }
   SDF_CUDA(dalloc((void**)&misc, 64));  // [0] changed flag, [6] max leaf distance, [7] values that do not fit
   SDF_CUDA(cudaMemsetAsync(misc, 0, 64, stream));
   SDF_CUDA(cudaEventRecord(ev0, stream));
@@ -378,27 +416,39 @@ cudaError_t compute_sdf_device(const WxTreeDesc& d, uint32_t* tab5_out, uint32_t
     sdf::LevelPass<uint16_t> L3{d.n3, vals3, nb3, F3, B3, misc, pass};
     SDF_CUDA((run_pass<3, uint16_t>(L3, stream, &rounds)));
   }
-  if (s5) sdf::merge_internal_kernel<<<blocks(s5), 256, 0, stream>>>(kids5, tab5, B5, s5, 15, out5);
-  if (s4) sdf::merge_internal_kernel<<<blocks(s4), 256, 0, stream>>>(kids4, tab4, B4, s4, 12, out4);
-  if (s3) {
-    if (tab3_elem_bytes == 1) sdf::merge_leaf_kernel<uint8_t><<<blocks(s3), 256, 0, stream>>>(vals3, B3, s3, (uint8_t*)out3, misc + 6, misc + 7);
-    else sdf::merge_leaf_kernel<uint32_t><<<blocks(s3), 256, 0, stream>>>(vals3, B3, s3, (uint32_t*)out3, misc + 6, misc + 7);
-  }
-  SDF_CUDA(cudaGetLastError());
-  SDF_CUDA(cudaEventRecord(ev1, stream));
-  if (s5) SDF_CUDA(cudaMemcpyAsync(tab5_out, out5, s5 * 4, cudaMemcpyDeviceToHost, stream));
-  if (s4) SDF_CUDA(cudaMemcpyAsync(tab4_out, out4, s4 * 4, cudaMemcpyDeviceToHost, stream));
-  if (s3) SDF_CUDA(cudaMemcpyAsync(tab3_out, out3, s3 * (tab3_elem_bytes == 1 ? 1 : 4), cudaMemcpyDeviceToHost, stream));
   uint32_t h_misc[16];
-  SDF_CUDA(cudaMemcpyAsync(h_misc, misc, 64, cudaMemcpyDeviceToHost, stream));
-  SDF_CUDA(cudaStreamSynchronize(stream));
-  if (device_ms) SDF_CUDA(cudaEventElapsedTime(device_ms, ev0, ev1));
-  // max tile distances of the internal levels: on the host, from the merged tables
   uint32_t m5 = 0, m4 = 0;
-  for (size_t i = 0; i < s5; ++i)
-    if (!((d.kids5[i >> 6] >> (i & 63)) & 1ull) && tab5_out[i] != 0xFFFFFFFEu) m5 = std::max(m5, tab5_out[i]);
-  for (size_t i = 0; i < s4; ++i)
-    if (!((d.kids4[i >> 6] >> (i & 63)) & 1ull) && tab4_out[i] != 0xFFFFFFFEu) m4 = std::max(m4, tab4_out[i]);
+  if (dev) {  // straight into the raycast kernel's tables
+    if (s5) sdf::pack_internal_kernel<<<blocks(s5), 256, 0, stream>>>(kids5, vals5, tab5, B5, s5, 15, 128.f, dev->e5, misc + 4);
+    if (s4) sdf::pack_internal_kernel<<<blocks(s4), 256, 0, stream>>>(kids4, vals4, tab4, B4, s4, 12, 8.f, dev->e4, misc + 5);
+    if (s3) sdf::pack_leaf_kernel<<<blocks(s3), 256, 0, stream>>>(vals3, B3, s3, dev->l3, misc + 6, misc + 7);
+    SDF_CUDA(cudaGetLastError());
+    SDF_CUDA(cudaEventRecord(ev1, stream));
+    SDF_CUDA(cudaMemcpyAsync(h_misc, misc, 64, cudaMemcpyDeviceToHost, stream));
+    SDF_CUDA(cudaStreamSynchronize(stream));
+    if (device_ms) SDF_CUDA(cudaEventElapsedTime(device_ms, ev0, ev1));
+    m5 = h_misc[4], m4 = h_misc[5];
+  } else {
+    if (s5) sdf::merge_internal_kernel<<<blocks(s5), 256, 0, stream>>>(kids5, tab5, B5, s5, 15, out5);
+    if (s4) sdf::merge_internal_kernel<<<blocks(s4), 256, 0, stream>>>(kids4, tab4, B4, s4, 12, out4);
+    if (s3) {
+      if (tab3_elem_bytes == 1) sdf::merge_leaf_kernel<uint8_t><<<blocks(s3), 256, 0, stream>>>(vals3, B3, s3, (uint8_t*)out3, misc + 6, misc + 7);
+      else sdf::merge_leaf_kernel<uint32_t><<<blocks(s3), 256, 0, stream>>>(vals3, B3, s3, (uint32_t*)out3, misc + 6, misc + 7);
+    }
+    SDF_CUDA(cudaGetLastError());
+    SDF_CUDA(cudaEventRecord(ev1, stream));
+    if (s5) SDF_CUDA(cudaMemcpyAsync(tab5_out, out5, s5 * 4, cudaMemcpyDeviceToHost, stream));
+    if (s4) SDF_CUDA(cudaMemcpyAsync(tab4_out, out4, s4 * 4, cudaMemcpyDeviceToHost, stream));
+    if (s3) SDF_CUDA(cudaMemcpyAsync(tab3_out, out3, s3 * (tab3_elem_bytes == 1 ? 1 : 4), cudaMemcpyDeviceToHost, stream));
+    SDF_CUDA(cudaMemcpyAsync(h_misc, misc, 64, cudaMemcpyDeviceToHost, stream));
+    SDF_CUDA(cudaStreamSynchronize(stream));
+    if (device_ms) SDF_CUDA(cudaEventElapsedTime(device_ms, ev0, ev1));
+    // max tile distances of the internal levels: on the host, from the merged tables
+    for (size_t i = 0; i < s5; ++i)
+      if (!((d.kids5[i >> 6] >> (i & 63)) & 1ull) && tab5_out[i] != 0xFFFFFFFEu) m5 = std::max(m5, tab5_out[i]);
+    for (size_t i = 0; i < s4; ++i)
+      if (!((d.kids4[i >> 6] >> (i & 63)) & 1ull) && tab4_out[i] != 0xFFFFFFFEu) m4 = std::max(m4, tab4_out[i]);
+  }
   info[0] = m5, info[1] = m4, info[2] = h_misc[6], info[3] = h_misc[7], info[4] = rounds;
   cleanup();
   return cudaSuccess;

@@ -153,8 +153,17 @@ void Renderer::change_vdb_model(vdb::VDB345& vdb, bool run_compute_sdf) {
   bool swept = false;
   last_sdf = WxSdfInfo{};
   if (run_compute_sdf && sdf_on_gpu) {
-    flat = vdb.to_flat();  // topology; the distances are filled in below
-    swept = compute_sdf_gpu(ctx_, flat, &last_sdf);
+    flat = vdb.to_flat();  // topology; the distances are computed on the device
+    const WxTreeDesc topo = flat.desc();
+    WxTree* built = nullptr;
+    const int rc = wx_tree_build(ctx_, &topo, &built, &last_sdf);  // sweep + device tables in one go
+    if (rc == WX_OK) {
+      if (tree_) wx_tree_free(ctx_, tree_);
+      tree_ = built;
+      return;
+    }
+    if (rc != WX_ERR_UNSUPPORTED) check(ctx_, rc, "wx_tree_build");
+    swept = compute_sdf_gpu(ctx_, flat, &last_sdf);  // leaf distances above 255: the two-call path has the u32 layout
     if (!swept) last_sdf = WxSdfInfo{};
   }
   if (!swept) {

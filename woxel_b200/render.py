@@ -99,6 +99,11 @@ class Context:
     def upload(self, flat_or_desc) -> "Tree":
         return Tree(self, flat_or_desc)
 
+    def build(self, flat_or_desc) -> "Tree":
+        """wx_tree_build: compute_sdf on the GPU + device tables in one call (the flat tree's distances are ignored).
+        The tree's `sdf` attribute holds the WxSdfInfo.  Raises WxError(-6) when a leaf distance exceeds 255."""
+        return Tree(self, flat_or_desc, build=True)
+
     def last_render_info(self) -> _ffi.WxRenderInfo:
         info = _ffi.WxRenderInfo()
         self.check(_ffi.cuda_lib().wx_last_render_info(self._h, C.byref(info)))
@@ -155,14 +160,19 @@ class Context:
 
 
 class Tree:
-    """wx_tree_upload / wx_tree_free."""
+    """wx_tree_upload (or wx_tree_build) / wx_tree_free."""
 
-    def __init__(self, ctx: Context, flat_or_desc):
+    def __init__(self, ctx: Context, flat_or_desc, build: bool = False):
         self._ctx = ctx
         self._keep = flat_or_desc  # keeps the host arrays alive during the call
         desc = flat_or_desc.desc if isinstance(flat_or_desc, FlatTree) else flat_or_desc
         self._h = C.c_void_p()
-        ctx.check(_ffi.cuda_lib().wx_tree_upload(ctx._h, C.byref(desc), C.byref(self._h)))
+        self.sdf = None
+        if build:
+            self.sdf = _ffi.WxSdfInfo()
+            ctx.check(_ffi.cuda_lib().wx_tree_build(ctx._h, C.byref(desc), C.byref(self._h), C.byref(self.sdf)))
+        else:
+            ctx.check(_ffi.cuda_lib().wx_tree_upload(ctx._h, C.byref(desc), C.byref(self._h)))
         self._keep = None
         self.info = _ffi.WxTreeInfo()
         ctx.check(_ffi.cuda_lib().wx_tree_info(self._h, C.byref(self.info)))
