@@ -117,6 +117,8 @@ struct LevelPass {
   V* F;                    // forward results  [n][SLOTS]
   V* B;                    // backward results [n][SLOTS]
   uint32_t* changed;       // set when a round lowers a value
+  const uint8_t* dirty_prev;  // [n]: the node changed in the previous round (nullptr: first round of a pass, sweep everything)
+  uint8_t* dirty_cur;         // [n]: set when this round lowers a value of the node
   int backward;
 };
 
@@ -139,7 +141,18 @@ __global__ void sweep_kernel(const LevelPass<V> L) {
   __shared__ uint32_t s_changed;
   const int tid = threadIdx.x;
   const uint32_t k = blockIdx.x;
-  if (tid < 27) s_nb[tid] = L.nb[(size_t)k * 27 + tid];
+  if (tid == 0) s_changed = 0u;
+  __syncthreads();
+  if (tid < 27) {
+    const int32_t j = L.nb[(size_t)k * 27 + tid];
+    s_nb[tid] = j;
+    // a node's sweep reads its own pass-initial values and its neighbours' current ones: it can only produce something
+    // new if a neighbour changed in the previous round
+    if (L.dirty_prev && j >= 0 && tid != 13 && L.dirty_prev[j]) s_changed = 1u;
+  }
+  __syncthreads();
+  if (L.dirty_prev && !s_changed) return;
+  __syncthreads();
   if (tid == 0) s_changed = 0u;
   __syncthreads();
 
@@ -216,7 +229,10 @@ __global__ void sweep_kernel(const LevelPass<V> L) {
   }
   if (lowered) s_changed = 1u;
   __syncthreads();
-  if (tid == 0 && s_changed) *L.changed = 1u;
+  if (tid == 0 && s_changed) {
+    *L.changed = 1u;
+    L.dirty_cur[k] = 1;
+  }
 }
 
 template <class V>
@@ -242,15 +258,22 @@ __global__ void merge_leaf_kernel(const uint64_t* vals3, const uint16_t* dist, s
   if (i >= total) return;
   const size_t node = i >> 9;
   const uint32_t o = (uint32_t)(i & 511u);
-  uint32_t d = 0;
+  uint32_t d = 0, m = 0, b = 0;
   if (!bit64(vals3 + node * 8, o)) {
     d = dist[i];
-    if (d == 0xFFFEu) d = 0xFFFFFFFEu;       // never reached: the reference leaves MAX - 1
-    else if (d >= 0x8000u) atomicAdd(bad, 1u);  // too close to the 16-bit sentinel to be trusted
-    if (d != 0xFFFFFFFEu) atomicMax(max_seen, d);
+    if (d == 0xFFFEu) d = 0xFFFFFFFEu;  // never reached: the reference leaves MAX - 1
+    else if (d >= 0x8000u) b = 1;       // too close to the 16-bit sentinel to be trusted
+    if (d != 0xFFFFFFFEu) m = d;
   }
-  if (sizeof(OUT) == 1 && d > 255u) atomicAdd(bad, 1u);
+  if (sizeof(OUT) == 1 && d > 255u) b = 1;
   out[i] = (OUT)d;
+  // one atomic per warp (the grid is a multiple of 32 threads; tail threads returned above only in the last warp)
+  const uint32_t act = __activemask();
+  m = __reduce_max_sync(act, m), b = __reduce_add_sync(act, b);
+  if ((threadIdx.x & 31u) == (uint32_t)(__ffs(act) - 1)) {
+    if (m) atomicMax(max_seen, m);
+    if (b) atomicAdd(bad, b);
+  }
 }
 
 // distances -> the raycast kernel's tables, on the device (wx_tree_build): the packing wx_tree_upload does on the host
@@ -276,13 +299,19 @@ __global__ void pack_internal_kernel(const uint64_t* kids, const uint64_t* vals,
 __global__ void pack_leaf_kernel(const uint64_t* vals3, const uint16_t* dist, size_t total, uint8_t* l3_out, uint32_t* max_seen, uint32_t* bad) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
-  uint32_t d = 0;
+  uint32_t d = 0, m = 0, b = 0;
   if (!bit64(vals3 + (i >> 9) * 8, (uint32_t)(i & 511u))) {
     d = dist[i];
-    if (d > 255u) atomicAdd(bad, 1u);  // needs the u32 brick layout: the caller falls back to wx_compute_sdf + wx_tree_upload
-    else atomicMax(max_seen, d);
+    if (d > 255u) b = 1;  // needs the u32 brick layout: the caller falls back to wx_compute_sdf + wx_tree_upload
+    else m = d;
   }
   l3_out[i] = (uint8_t)d;
+  const uint32_t act = __activemask();
+  m = __reduce_max_sync(act, m), b = __reduce_add_sync(act, b);
+  if ((threadIdx.x & 31u) == (uint32_t)(__ffs(act) - 1)) {
+    if (m) atomicMax(max_seen, m);
+    if (b) atomicAdd(bad, b);
+  }
 }
 
 }  // namespace sdf
@@ -323,9 +352,13 @@ static cudaError_t run_pass(sdf::LevelPass<V> L, cudaStream_t stream, uint32_t* 
     e = cudaGetLastError();
   }
   if (e != cudaSuccess) return e;
+  uint8_t* dirty[2] = {L.dirty_cur, const_cast<uint8_t*>(L.dirty_prev)};  // the caller passes two scratch arrays of n bytes
   for (uint32_t r = 0; r < 100000u; ++r) {
     e = cudaMemsetAsync(L.changed, 0, sizeof(uint32_t), stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(dirty[r & 1], 0, L.n, stream);
     if (e != cudaSuccess) return e;
+    L.dirty_cur = dirty[r & 1];
+    L.dirty_prev = r == 0 ? nullptr : dirty[(r & 1) ^ 1];
     sdf::sweep_kernel<LOG2D, V><<<L.n, threads, smem, stream>>>(L);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
@@ -394,7 +427,11 @@ cudaError_t compute_sdf_device(const WxTreeDesc& d, uint32_t* tab5_out, uint32_t
     SDF_CUDA(dalloc((void**)&out4, s4 * 4));
     SDF_CUDA(dalloc(&out3, s3 * (tab3_elem_bytes == 1 ? 1 : 4)));
   }
-  SDF_CUDA(dalloc((void**)&misc, 64));  // [0] changed flag, [6] max leaf distance, [7] values that do not fit
+  uint8_t *dirty_a, *dirty_b;
+  const size_t n_max = std::max<size_t>(std::max<size_t>(d.n5, d.n4), d.n3);
+  SDF_CUDA(dalloc((void**)&dirty_a, n_max));
+  SDF_CUDA(dalloc((void**)&dirty_b, n_max));
+  SDF_CUDA(dalloc((void**)&misc, 64));  // [0] changed flag, [4..6] max distance per level, [7] values that do not fit
   SDF_CUDA(cudaMemsetAsync(misc, 0, 64, stream));
   SDF_CUDA(cudaEventRecord(ev0, stream));
 
@@ -409,11 +446,11 @@ cudaError_t compute_sdf_device(const WxTreeDesc& d, uint32_t* tab5_out, uint32_t
 
   uint32_t rounds = 0;
   for (int pass = 0; pass < 2; ++pass) {
-    sdf::LevelPass<uint32_t> L5{d.n5, kids5, nb5, F5, B5, misc, pass};
+    sdf::LevelPass<uint32_t> L5{d.n5, kids5, nb5, F5, B5, misc, dirty_b, dirty_a, pass};
     SDF_CUDA((run_pass<5, uint32_t>(L5, stream, &rounds)));
-    sdf::LevelPass<uint32_t> L4{d.n4, kids4, nb4, F4, B4, misc, pass};
+    sdf::LevelPass<uint32_t> L4{d.n4, kids4, nb4, F4, B4, misc, dirty_b, dirty_a, pass};
     SDF_CUDA((run_pass<4, uint32_t>(L4, stream, &rounds)));
-    sdf::LevelPass<uint16_t> L3{d.n3, vals3, nb3, F3, B3, misc, pass};
+    sdf::LevelPass<uint16_t> L3{d.n3, vals3, nb3, F3, B3, misc, dirty_b, dirty_a, pass};
     SDF_CUDA((run_pass<3, uint16_t>(L3, stream, &rounds)));
   }
   uint32_t h_misc[16];
