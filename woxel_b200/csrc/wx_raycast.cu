@@ -13,7 +13,18 @@ namespace wx {
 #ifndef WX_CTA_WARPS
 #define WX_CTA_WARPS 4  // 4: CTA = 2x2 warp tiles (16x8 px); 2: 2x1 (16x4 px); 1: one tile (8x4 px)
 #endif
-constexpr int kTileW = WX_CTA_WARPS >= 2 ? 16 : 8, kTileH = WX_CTA_WARPS >= 8 ? 16 : (WX_CTA_WARPS >= 4 ? 8 : 4);  // CTA footprint in pixels
+#ifndef WX_WARP_W
+// Pixels per warp row: a warp covers WX_WARP_W x (32 / WX_WARP_W) pixels.  The reference's workgroup is 8 x 4; measured on
+// the 4K sphere (profiles/r1_variants_g.txt): 1x32 1.038 ms, 2x16 0.963, 4x8 0.925, 8x4 0.948, 16x2 1.002, 32x1 1.108.
+#define WX_WARP_W 4
+#endif
+constexpr int kWarpW = WX_WARP_W, kWarpH = 32 / WX_WARP_W;
+// the warps of a CTA tile a 16-pixel-wide block (8 rows for 4 warps): row bands of 8 stay the sharding unit
+constexpr int kCtaWarpsX = (16 / kWarpW) < WX_CTA_WARPS ? (16 / kWarpW) : WX_CTA_WARPS;
+constexpr int kCtaWarpsY = WX_CTA_WARPS / kCtaWarpsX;
+constexpr int kTileW = kCtaWarpsX * kWarpW, kTileH = kCtaWarpsY * kWarpH;  // CTA footprint in pixels
+#define WX_LANE_X(warp, lane) (((warp) % kCtaWarpsX) * kWarpW + ((lane) % kWarpW))
+#define WX_LANE_Y(warp, lane) (((warp) / kCtaWarpsX) * kWarpH + ((lane) / kWarpW))
 constexpr int kThreads = 32 * WX_CTA_WARPS;
 #ifndef WX_MIN_BLOCKS
 #define WX_MIN_BLOCKS (36 / WX_CTA_WARPS)  // resident CTAs per SM the register budget is capped for (36 warps -> 56 registers)
@@ -98,8 +109,8 @@ __global__ void __launch_bounds__(kThreads, WX_MIN_BLOCKS) raycast_kernel(const 
   else if (P.own_bands > 1u) own_band = trow / P.tile_rows_per_band, in_band = trow - own_band * P.tile_rows_per_band;
   const uint32_t band = own_band * P.shard_count + P.shard_index;
   PixelRef q;
-  q.x = tx * kTileW + (warp & 1) * 8 + (lane & 7);
-  q.y = P.row_base + band * P.band_rows + in_band * kTileH + (warp >> 1) * 4 + (lane >> 3);
+  q.x = tx * kTileW + WX_LANE_X(warp, lane);
+  q.y = P.row_base + band * P.band_rows + in_band * kTileH + WX_LANE_Y(warp, lane);
   q.cam = P.cam_base + blockIdx.z;
   q.in_frame = q.x < P.width && q.y < P.row_end;
   q.dispatched = q.x < P.disp_w && q.y < P.disp_h;
