@@ -420,3 +420,55 @@ def test_large_camera_batch_mixed_modes(gpu_ctx):
         assert np.array_equal(batch[k], single[0]), k
     ref, _, _ = scenes.get_scene(name).gpu.render(scenes.state_for((0.5, 20.5, -169.5), (0.5, 0.5, 0.5), w, h, mode=int(states[0].render_mode[0])), w, h, aov=False)
     assert np.array_equal(batch[0], ref)
+
+
+@pytest.mark.parametrize("mode", [1, 2, 4])
+def test_assets_1080p_remaining_modes(gpu_ctx, mode):
+    """BASELINE config 2 at full size for the modes test_assets_1080p leaves out."""
+    eye, target = scenes.CAMERAS["oblique_a"]
+    check_frame(gpu_ctx, "icosahedron", scenes.state_for(eye, target, 1920, 1080, mode=mode, show_grid=(1, 1, 1)), 1920, 1080)
+
+
+def test_config3_full_size_torus(gpu_ctx):
+    """BASELINE config 3 at its full size: the procedural 2048^3 torus at 3840x2160.  Model load through wx_tree_build
+    (GPU sweep), one frame against the oracle (rendering from the host sweep's tables), and the size-independent
+    properties: rendering twice gives the same bytes; three row-band shards reassemble the frame; a 2-camera batch
+    equals two single frames."""
+    import ctypes as C
+    from woxel_b200 import _ffi
+    w, h = 3840, 2160
+    v = W.VDB345.torus()
+    tree = gpu_ctx.build(v.to_flat(narrow_leaves=False))
+    v.compute_sdf()
+    f = v.to_flat(narrow_leaves=False)
+    g = O.gpudata_from_tables(f.origins, f.kids5, f.vals5, f.tab5, f.kids4, f.vals4, f.tab4, f.vals3, f.tab3)
+    try:
+        assert list(tree.info.max_dist) == [int(f.tab5[~scenes.bits2d(f.kids5)].max()), int(f.tab4[~scenes.bits2d(f.kids4)].max()),
+                                             int(f.tab3[~scenes.bits2d(f.vals3)].max())]
+        st = scenes.state_for((0.5, 0.5, -2500.5), (0.5, 0.5, 0.5), w, h, mode=0)
+        a, _ = gpu_ctx.render(tree, to_wx(st), w, h)
+        ref, _, stats = g.render(st, w, h, aov=False)
+        assert stats.hit > 500000 and stats.maxed == 0
+        assert np.array_equal(a[0], ref)
+        b, _ = gpu_ctx.render(tree, to_wx(st), w, h)
+        assert np.array_equal(a, b)
+        st2 = scenes.state_for((1800.5, 900.5, -1700.5), (0.5, 0.5, 0.5), w, h, mode=3)
+        pair, _ = gpu_ctx.render(tree, [to_wx(st), to_wx(st2)], w, h)
+        assert np.array_equal(pair[0], a[0])
+        single2, _ = gpu_ctx.render(tree, to_wx(st2), w, h)
+        assert np.array_equal(pair[1], single2[0])
+        lib = _ffi.cuda_lib()
+        buf = C.c_void_p()
+        gpu_ctx.check(lib.wx_device_alloc(gpu_ctx._h, 0, w * h * 4, C.byref(buf)))
+        try:
+            for idx in range(3):
+                gpu_ctx.render_device(tree, to_wx(st), w, h, buf.value, shard=(idx, 3, 16))
+            out = np.zeros((h, w, 4), np.uint8)
+            gpu_ctx.check(lib.wx_stream_synchronize(gpu_ctx._h, 0, None))
+            gpu_ctx.check(lib.wx_memcpy_d2h(gpu_ctx._h, 0, out.ctypes.data, buf, w * h * 4, None))
+            gpu_ctx.check(lib.wx_stream_synchronize(gpu_ctx._h, 0, None))
+            assert np.array_equal(out, a[0])
+        finally:
+            lib.wx_device_free(gpu_ctx._h, 0, buf)
+    finally:
+        tree.free()
