@@ -281,6 +281,39 @@ def test_multi_device_context_equals_single_device():
         one.close(), many.close()
 
 
+@pytest.mark.skipif(_device_count() < 2, reason="needs two GPUs")
+@pytest.mark.parametrize("shape", [(640, 360, 1), (328, 203, 5), (1280, 824, 1), (96, 44, 19), (64, 4, 2)])
+def test_multi_device_distributed_readback(shape):
+    """Without AOVs every GPU reads its own row bands back over its own PCIe link (frames, heights that are not a
+    multiple of the band height, fewer bands than GPUs, more cameras than pipeline chunks); wx_capture_srgb afterwards
+    completes device 0's frame over NVLink.  Everything must equal the single-device results."""
+    w, h, n_cam = shape
+    s = scenes.get_scene("icosahedron")
+    cams = [scenes.CAMERAS["default"], scenes.CAMERAS["oblique_a"], scenes.CAMERAS["oblique_b"]]
+    states = [to_wx(scenes.state_for(*cams[k % 3], w, h, mode=(0, 3, 4, 1, 2)[k % 5])) for k in range(n_cam)]
+    one = W.Context()
+    try:
+        t1 = one.upload(s.desc())
+        a, _ = one.render(t1, states, w, h)
+        a_rgb = one.capture_srgb(n_cam, w, h)
+        t1.free()
+    finally:
+        one.close()
+    for n in sorted({2, _device_count()}):
+        many = W.Context(n_devices=n)
+        try:
+            tn = many.upload(s.desc())
+            out = np.full((n_cam, h, w, 4), 0xAB, np.uint8)
+            b, _ = many.render(tn, states, w, h, out=out)
+            assert np.array_equal(a, b), f"{n} devices"
+            assert np.array_equal(many.capture_srgb(n_cam, w, h), a_rgb), f"{n} devices: capture after the lazy gather"
+            b2, _ = many.render(tn, states, w, h)  # a second call reuses the per-device frames
+            assert np.array_equal(a, b2)
+            tn.free()
+        finally:
+            many.close()
+
+
 def _product_scene(kind):
     """A procedural scene of the benchmark configs built by the PRODUCT host (set_voxel tree -> compute_sdf -> to_flat);
     the oracle renders from the same tables (its own compute_sdf is compared with the product's in test_host_vs_oracle)."""
