@@ -714,30 +714,39 @@ static int render_distributed(WxContext* ctx, const WxTree* tree, const WxState*
       WX_CUDA(ctx, cudaMemcpyAsync(s.d_states, states, (size_t)n_states * sizeof(WxState), cudaMemcpyHostToDevice, s.stream));
     }
     WX_CUDA(ctx, cudaEventRecord(s.ev0, s.stream));
-    WX_CUDA(ctx, cudaEventRecord(s.fork, s.stream));
-    cudaStream_t ks[3] = {s.stream, s.aux[0], s.aux[1]};
-    for (int k = 0; k < 2; ++k) WX_CUDA(ctx, cudaStreamWaitEvent(s.aux[k], s.fork, 0));
     WxShard sh{(uint32_t)i, (uint32_t)ndev, (uint32_t)kBandRowsMultiple, 0};
-    uint32_t c_idx = 0;
-    for (uint32_t c0 = 0; c0 < n_states; c0 += per, ++c_idx) {
-      const uint32_t c1 = std::min(n_states, c0 + per);
-      cudaStream_t st = ks[c_idx % 3];
+    s.events_pending = true;
+    if (n_chunks == 1) {  // one frame: kernel and copy in stream order, nothing to overlap (and the fewest host calls)
       uint32_t l = 0;
-      int rc = launch_on(ctx, i, tree, states, n_states, width, height, local, nullptr, &sh, st, &l, c0, c1 - c0, 0, 0, n_states > 1);
+      int rc = launch_on(ctx, i, tree, states, n_states, width, height, local, nullptr, &sh, s.stream, &l);
       if (rc) return rc;
       *launches += l;
-      WX_CUDA(ctx, cudaEventRecord(s.chunk_done[c_idx], st));
-      WX_CUDA(ctx, cudaStreamWaitEvent(s.copy_stream, s.chunk_done[c_idx], 0));
-      WX_CUDA(ctx, copy_own_bands(rgba_out, local, i, ndev, c0, c1, width, height, cudaMemcpyDeviceToHost, s.copy_stream));
+      WX_CUDA(ctx, cudaEventRecord(s.ev1, s.stream));
+      WX_CUDA(ctx, copy_own_bands(rgba_out, local, i, ndev, 0, n_states, width, height, cudaMemcpyDeviceToHost, s.stream));
+    } else {
+      WX_CUDA(ctx, cudaEventRecord(s.fork, s.stream));
+      cudaStream_t ks[3] = {s.stream, s.aux[0], s.aux[1]};
+      for (int k = 0; k < 2; ++k) WX_CUDA(ctx, cudaStreamWaitEvent(s.aux[k], s.fork, 0));
+      uint32_t c_idx = 0;
+      for (uint32_t c0 = 0; c0 < n_states; c0 += per, ++c_idx) {
+        const uint32_t c1 = std::min(n_states, c0 + per);
+        cudaStream_t st = ks[c_idx % 3];
+        uint32_t l = 0;
+        int rc = launch_on(ctx, i, tree, states, n_states, width, height, local, nullptr, &sh, st, &l, c0, c1 - c0, 0, 0, true);
+        if (rc) return rc;
+        *launches += l;
+        WX_CUDA(ctx, cudaEventRecord(s.chunk_done[c_idx], st));
+        WX_CUDA(ctx, cudaStreamWaitEvent(s.copy_stream, s.chunk_done[c_idx], 0));
+        WX_CUDA(ctx, copy_own_bands(rgba_out, local, i, ndev, c0, c1, width, height, cudaMemcpyDeviceToHost, s.copy_stream));
+      }
+      for (int k = 0; k < 2; ++k) {
+        WX_CUDA(ctx, cudaEventRecord(s.join[k], s.aux[k]));
+        WX_CUDA(ctx, cudaStreamWaitEvent(s.stream, s.join[k], 0));
+      }
+      WX_CUDA(ctx, cudaEventRecord(s.ev1, s.stream));  // all kernels of this device
+      WX_CUDA(ctx, cudaEventRecord(s.fork, s.copy_stream));
+      WX_CUDA(ctx, cudaStreamWaitEvent(s.stream, s.fork, 0));
     }
-    for (int k = 0; k < 2; ++k) {
-      WX_CUDA(ctx, cudaEventRecord(s.join[k], s.aux[k]));
-      WX_CUDA(ctx, cudaStreamWaitEvent(s.stream, s.join[k], 0));
-    }
-    WX_CUDA(ctx, cudaEventRecord(s.ev1, s.stream));  // all kernels of this device
-    s.events_pending = true;
-    WX_CUDA(ctx, cudaEventRecord(s.fork, s.copy_stream));
-    WX_CUDA(ctx, cudaStreamWaitEvent(s.stream, s.fork, 0));
     WX_CUDA(ctx, cudaEventRecord(s.join[0], s.stream));  // kernels and copies of this device
   }
   WX_CUDA(ctx, cudaSetDevice(d0.id));
