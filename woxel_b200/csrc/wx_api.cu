@@ -548,7 +548,8 @@ extern "C" int wx_tree_info(const WxTree* tree, WxTreeInfo* info) {
 // ---------------------------------------------------------------------------------------------
 // Frame entry points
 // ---------------------------------------------------------------------------------------------
-// Frames [cam0, cam0 + ncam) of `states`, rows [row0, row1) (row1 == 0: all rows; ignored when sharded).
+// Frames [cam0, cam0 + ncam) of `states`, rows [row0, row1) (row1 == 0: all rows; with a shard row0 must be a multiple of
+// one round of the band deal, shard->count * shard->band_rows).
 // `states_on_device`: the whole batch is already in s.d_states (a pipelined wx_render uploads it once).
 static int launch_on(WxContext* ctx, int dev_i, const WxTree* tree, const WxState* states, uint32_t n_states, uint32_t width,
                      uint32_t height, uint8_t* rgba_dev, const WxAov* aov_dev, const WxShard* shard, cudaStream_t stream,
@@ -658,21 +659,22 @@ static int ensure(WxContext* ctx, void** p, size_t* have, size_t need) {
 }
 
 
-// The bands of device `i` in frames [cam0, cam1): one strided copy per frame (pitch = one round of the deal) plus the
-// frame's last, partial band when it falls to this device.  `dst` and `src` have the frame layout.
-static cudaError_t copy_own_bands(uint8_t* dst, const uint8_t* src, int i, int ndev, uint32_t cam0, uint32_t cam1, uint32_t width,
-                                  uint32_t height, cudaMemcpyKind kind, cudaStream_t st) {
+// The bands of device `i` in rows [row0, row1) (row0 a multiple of one round of the deal) of frames [cam0, cam1): one
+// strided copy per frame (pitch = one round of the deal) plus the last, partial band when it falls to this device.
+// `dst` and `src` have the frame layout.
+static cudaError_t copy_own_bands(uint8_t* dst, const uint8_t* src, int i, int ndev, uint32_t cam0, uint32_t cam1, uint32_t row0,
+                                  uint32_t row1, uint32_t width, uint32_t height, cudaMemcpyKind kind, cudaStream_t st) {
   const size_t band_bytes = (size_t)kBandRowsMultiple * width * 4, frame_bytes = (size_t)height * width * 4;
-  const uint32_t full = height / kBandRowsMultiple, tail_rows = height % kBandRowsMultiple;
+  const uint32_t rows = row1 - row0, full = rows / kBandRowsMultiple, tail_rows = rows % kBandRowsMultiple;
   const uint32_t own_full = full > (uint32_t)i ? (full - (uint32_t)i + (uint32_t)ndev - 1) / (uint32_t)ndev : 0;
   for (uint32_t c = cam0; c < cam1; ++c) {
-    const size_t off = (size_t)c * frame_bytes + (size_t)i * band_bytes;
+    const size_t base = (size_t)c * frame_bytes + (size_t)row0 * width * 4, off = base + (size_t)i * band_bytes;
     if (own_full) {
       cudaError_t e = cudaMemcpy2DAsync(dst + off, (size_t)ndev * band_bytes, src + off, (size_t)ndev * band_bytes, band_bytes, own_full, kind, st);
       if (e != cudaSuccess) return e;
     }
     if (tail_rows && full % (uint32_t)ndev == (uint32_t)i) {
-      const size_t toff = (size_t)c * frame_bytes + (size_t)full * band_bytes;
+      const size_t toff = base + (size_t)full * band_bytes;
       cudaError_t e = cudaMemcpyAsync(dst + toff, src + toff, (size_t)tail_rows * width * 4, kind, st);
       if (e != cudaSuccess) return e;
     }
@@ -688,7 +690,22 @@ static int render_distributed(WxContext* ctx, const WxTree* tree, const WxState*
   const int ndev = (int)ctx->dev.size();
   const size_t npix = (size_t)n_states * width * height;
   DeviceSlot& d0 = ctx->dev[0];
-  const uint32_t n_chunks = std::min<uint32_t>(n_states, 16u), per = (n_states + n_chunks - 1) / n_chunks;
+  // Pipeline units: groups of cameras, or -- one large frame -- 4 / 2 / 2 row blocks on 2 / 4 / 8 devices, each whole
+  // rounds of the deal (more blocks cost more in host calls per device than the overlap returns: profiles/r1_multi_device_n8.txt).
+  struct Chunk {
+    uint32_t cam0, cam1, row0, row1;
+  };
+  std::vector<Chunk> chunks;
+  if (n_states > 1) {
+    const uint32_t k = std::min<uint32_t>(n_states, 16u), per = (n_states + k - 1) / k;
+    for (uint32_t c = 0; c < n_states; c += per) chunks.push_back(Chunk{c, std::min(n_states, c + per), 0, height});
+  } else {
+    static const uint32_t k_env = getenv("WX_RENDER_CHUNKS") ? (uint32_t)atoi(getenv("WX_RENDER_CHUNKS")) : 0u;  // experiment knob
+    const uint32_t k = k_env ? k_env : ((uint64_t)width * height >= (1u << 20) ? std::max(2u, 8u / (uint32_t)ndev) : 1u);
+    const uint32_t round = (uint32_t)ndev * kBandRowsMultiple, rows = ((height + k - 1) / k + round - 1) / round * round;
+    for (uint32_t r = 0; r < height; r += rows) chunks.push_back(Chunk{0, 1, r, std::min(height, r + rows)});
+  }
+  const uint32_t n_chunks = (uint32_t)chunks.size();
   for (int i = 0; i < ndev; ++i) {
     DeviceSlot& s = ctx->dev[i];
     WX_CUDA(ctx, cudaSetDevice(s.id));
@@ -716,28 +733,28 @@ static int render_distributed(WxContext* ctx, const WxTree* tree, const WxState*
     WX_CUDA(ctx, cudaEventRecord(s.ev0, s.stream));
     WxShard sh{(uint32_t)i, (uint32_t)ndev, (uint32_t)kBandRowsMultiple, 0};
     s.events_pending = true;
-    if (n_chunks == 1) {  // one frame: kernel and copy in stream order, nothing to overlap (and the fewest host calls)
+    if (n_chunks == 1) {  // kernel and copy in stream order, nothing to overlap (and the fewest host calls)
       uint32_t l = 0;
       int rc = launch_on(ctx, i, tree, states, n_states, width, height, local, nullptr, &sh, s.stream, &l);
       if (rc) return rc;
       *launches += l;
       WX_CUDA(ctx, cudaEventRecord(s.ev1, s.stream));
-      WX_CUDA(ctx, copy_own_bands(rgba_out, local, i, ndev, 0, n_states, width, height, cudaMemcpyDeviceToHost, s.stream));
+      WX_CUDA(ctx, copy_own_bands(rgba_out, local, i, ndev, 0, n_states, 0, height, width, height, cudaMemcpyDeviceToHost, s.stream));
     } else {
       WX_CUDA(ctx, cudaEventRecord(s.fork, s.stream));
       cudaStream_t ks[3] = {s.stream, s.aux[0], s.aux[1]};
       for (int k = 0; k < 2; ++k) WX_CUDA(ctx, cudaStreamWaitEvent(s.aux[k], s.fork, 0));
-      uint32_t c_idx = 0;
-      for (uint32_t c0 = 0; c0 < n_states; c0 += per, ++c_idx) {
-        const uint32_t c1 = std::min(n_states, c0 + per);
+      for (uint32_t c_idx = 0; c_idx < n_chunks; ++c_idx) {
+        const Chunk& ch = chunks[c_idx];
         cudaStream_t st = ks[c_idx % 3];
         uint32_t l = 0;
-        int rc = launch_on(ctx, i, tree, states, n_states, width, height, local, nullptr, &sh, st, &l, c0, c1 - c0, 0, 0, true);
+        int rc = launch_on(ctx, i, tree, states, n_states, width, height, local, nullptr, &sh, st, &l, ch.cam0, ch.cam1 - ch.cam0, ch.row0,
+                           ch.row1, n_states > 1);
         if (rc) return rc;
         *launches += l;
         WX_CUDA(ctx, cudaEventRecord(s.chunk_done[c_idx], st));
         WX_CUDA(ctx, cudaStreamWaitEvent(s.copy_stream, s.chunk_done[c_idx], 0));
-        WX_CUDA(ctx, copy_own_bands(rgba_out, local, i, ndev, c0, c1, width, height, cudaMemcpyDeviceToHost, s.copy_stream));
+        WX_CUDA(ctx, copy_own_bands(rgba_out, local, i, ndev, ch.cam0, ch.cam1, ch.row0, ch.row1, width, height, cudaMemcpyDeviceToHost, s.copy_stream));
       }
       for (int k = 0; k < 2; ++k) {
         WX_CUDA(ctx, cudaEventRecord(s.join[k], s.aux[k]));
@@ -762,8 +779,8 @@ static int gather_frame(WxContext* ctx) {
   for (int i = 1; i < ndev; ++i) {
     DeviceSlot& s = ctx->dev[i];
     WX_CUDA(ctx, cudaSetDevice(s.id));
-    WX_CUDA(ctx, copy_own_bands(ctx->fb.rgba, s.scratch, i, ndev, 0, ctx->fb.dist_states, ctx->fb.dist_width, ctx->fb.dist_height,
-                                cudaMemcpyDefault, s.stream));
+    WX_CUDA(ctx, copy_own_bands(ctx->fb.rgba, s.scratch, i, ndev, 0, ctx->fb.dist_states, 0, ctx->fb.dist_height, ctx->fb.dist_width,
+                                ctx->fb.dist_height, cudaMemcpyDefault, s.stream));
     WX_CUDA(ctx, cudaEventRecord(s.join[0], s.stream));
   }
   WX_CUDA(ctx, cudaSetDevice(d0.id));

@@ -208,8 +208,11 @@ cudaError_t launch_raycast(RenderParams& P, uint32_t n_cams, uint32_t render_mod
     P.shard_count = 1, P.shard_index = 0;
     P.own_bands = 1;
   } else {
-    P.row_base = 0, P.row_end = P.height;  // row ranges and band dealing do not combine
-    P.own_bands = shard_own_bands(P.height, P.shard_index, P.shard_count, P.band_rows);
+    // Band dealing over a row range: only from a row where the deal starts over (a multiple of one round of bands),
+    // so that a band belongs to the same shard as in the whole frame.
+    if (P.row_base % (P.shard_count * P.band_rows) != 0u) return cudaErrorInvalidValue;
+    if (P.row_base >= P.row_end) return cudaSuccess;
+    P.own_bands = shard_own_bands(P.row_end - P.row_base, P.shard_index, P.shard_count, P.band_rows);
   }
   P.tiles_x = (P.width + kTileW - 1) / kTileW;
   P.tile_rows_per_band = P.band_rows / kTileH;
