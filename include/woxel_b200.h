@@ -136,7 +136,9 @@ int wx_abi_version(void);
 const char *wx_strerror(int status);
 const char *wx_last_error(const WxContext *ctx); /* detail text of the last failure on this context */
 
-/* n_devices == 0: use the current device only.  device_ids may be NULL (0..n_devices-1). */
+/* n_devices == 0: use the current device only.  device_ids may be NULL (0..n_devices-1).  A device id may be listed more
+ * than once: every entry gets its own streams, frame and tree replica and takes its share of the row bands, which lets the
+ * multi-device code paths be exercised on a single GPU. */
 int wx_init(int n_devices, const int *device_ids, WxContext **out);
 int wx_shutdown(WxContext *ctx);
 int wx_device_count(const WxContext *ctx);

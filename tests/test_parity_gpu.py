@@ -255,15 +255,27 @@ def test_pipelined_readback_equals_single_launch(gpu_ctx):
         assert np.array_equal(plain[0], ref)
 
 
-@pytest.mark.skipif(_device_count() < 2, reason="needs two GPUs")
-def test_multi_device_context_equals_single_device():
+def _multi_contexts():
+    """Device lists for the multi-device tests: 2 and all GPUs of the box; on a single-GPU box the same GPU listed 2 and
+    3 times (wx_init gives every entry its own streams, frame and tree replica, so the sharding, the per-device
+    read-back and the gather run exactly as on several GPUs)."""
+    n = _device_count()
+    if n >= 2:
+        return [list(range(k)) for k in sorted({2, n})]
+    return [[0, 0], [0, 0, 0]]
+
+
+@pytest.mark.parametrize("which", [0, 1])
+def test_multi_device_context_equals_single_device(which):
     """One frame / one camera batch split by row bands over every GPU of the box, stored into device 0's frame over
     NVLink by the kernels themselves: identical to the single-device frame."""
-    n = _device_count()
+    lists = _multi_contexts()
+    ids = lists[min(which, len(lists) - 1)]
+    n = len(ids)
     name, w, h = "icosahedron", 640, 360
     s = scenes.get_scene(name)
     one = W.Context()
-    many = W.Context(n_devices=n)
+    many = W.Context(n_devices=n, device_ids=ids)
     try:
         assert many.device_count == n
         t1, tn = one.upload(s.desc()), many.upload(s.desc())
@@ -281,7 +293,6 @@ def test_multi_device_context_equals_single_device():
         one.close(), many.close()
 
 
-@pytest.mark.skipif(_device_count() < 2, reason="needs two GPUs")
 @pytest.mark.parametrize("shape", [(640, 360, 1), (328, 203, 5), (1280, 824, 1), (96, 44, 19), (64, 4, 2)])
 def test_multi_device_distributed_readback(shape):
     """Without AOVs every GPU reads its own row bands back over its own PCIe link (frames, heights that are not a
@@ -299,8 +310,9 @@ def test_multi_device_distributed_readback(shape):
         t1.free()
     finally:
         one.close()
-    for n in sorted({2, _device_count()}):
-        many = W.Context(n_devices=n)
+    for ids in _multi_contexts():
+        n = len(ids)
+        many = W.Context(n_devices=n, device_ids=ids)
         try:
             tn = many.upload(s.desc())
             out = np.full((n_cam, h, w, 4), 0xAB, np.uint8)

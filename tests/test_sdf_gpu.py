@@ -101,6 +101,30 @@ def test_tree_build_equals_sweep_plus_upload(gpu_ctx, name):
         built.free(), plain.free()
 
 
+def test_tree_build_replicates_to_every_device(gpu_ctx):
+    """wx_tree_build on a multi-device context: the tables packed on device 0 are copied to the other devices (on a
+    single-GPU box: the same GPU listed three times), and the band-sharded frame equals the single-device one."""
+    import torch
+    n = torch.cuda.device_count()
+    ids = list(range(n)) if n >= 2 else [0, 0, 0]
+    s = scenes.get_scene("icosahedron")
+    many = W.Context(n_devices=len(ids), device_ids=ids)
+    built1 = gpu_ctx.build(topo_desc(s))
+    try:
+        built = many.build(topo_desc(s))
+        eye, target = scenes.CAMERAS["oblique_b"]
+        st = W.ComputeState.from_buffer_copy(bytes(scenes.state_for(eye, target, 512, 264, mode=3)))
+        a, aov_a = gpu_ctx.render(built1, st, 512, 264, aov=True)
+        b, aov_b = many.render(built, st, 512, 264, aov=True)
+        c, _ = many.render(built, st, 512, 264)
+        assert np.array_equal(a, b) and np.array_equal(a, c)
+        for key in ("state", "voxel", "leaf", "iters"):
+            assert np.array_equal(aov_a[key], aov_b[key]), key
+        built.free()
+    finally:
+        built1.free(), many.close()
+
+
 def test_tree_build_reports_wide_leaves(gpu_ctx):
     """A chain of empty leaves pushes a leaf distance above 255: wx_tree_build says so, the two-call path handles it."""
     t = O.Tree()

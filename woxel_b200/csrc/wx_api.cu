@@ -165,7 +165,9 @@ extern "C" int wx_init(int n_devices, const int* device_ids, WxContext** out) {
       wx_shutdown(ctx);
       return rc;
     }
-    if (i > 0) {
+    if (i > 0 && s.id == ctx->dev[0].id) {
+      s.peer_to_first = true;  // the same GPU listed again (a second set of streams, frame and tree replica): plain stores
+    } else if (i > 0) {
       int can = 0;
       if (cudaDeviceCanAccessPeer(&can, s.id, ctx->dev[0].id) == cudaSuccess && can) {
         cudaError_t pe = cudaDeviceEnablePeerAccess(ctx->dev[0].id, 0);
