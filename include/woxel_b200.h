@@ -111,7 +111,7 @@ typedef struct WxAov {
 } WxAov;
 
 /* Which rows of every frame this call renders: bands of `band_rows` rows, band b belongs to shard
- * (b % count); index/count = 0/1 renders everything.  band_rows must be a multiple of 4. */
+ * (b % count); index/count = 0/1 renders everything.  band_rows must be a multiple of 8. */
 typedef struct WxShard {
   uint32_t index, count, band_rows, reserved;
 } WxShard;
