@@ -14,7 +14,8 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_DIR = os.path.join(ROOT, "oracle")
 # WXO_VARIANT=fma loads the FMA-contracted sensitivity build (oracle/Makefile); the default is the strict-IEEE oracle
-_VARIANT = "libwxo_fma.so" if os.environ.get("WXO_VARIANT") == "fma" else "libwxo.so"
+# WXO_VARIANT=asan loads the AddressSanitizer/UBSan build (tools/asan_host.sh)
+_VARIANT = {"fma": "libwxo_fma.so", "asan": "libwxo_asan.so"}.get(os.environ.get("WXO_VARIANT", ""), "libwxo.so")
 LIB_PATH = os.path.join(ORACLE_DIR, _VARIANT)
 
 EP_OFFS, EP_LEAF, EP_INNR5, EP_INNR4, EP_ROOT, EP_BKGR = range(6)

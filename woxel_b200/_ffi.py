@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # WOXEL_B200_LIB: load another build of the same library (kernel experiments, tools/variants.sh)
 CUDA_LIB_PATH = os.environ.get("WOXEL_B200_LIB") or os.path.join(_HERE, "libwoxel_b200.so")
-HOST_LIB_PATH = os.path.join(_HERE, "libwoxel_host.so")
+HOST_LIB_PATH = os.environ.get("WOXEL_HOST_LIB") or os.path.join(_HERE, "libwoxel_host.so")  # override: sanitizer builds (tools/asan_host.sh)
 
 
 class WxTreeDesc(C.Structure):

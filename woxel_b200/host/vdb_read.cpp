@@ -39,7 +39,7 @@ struct VdbReader::Cursor {
   }
   void bytes(void* dst, size_t n) {
     need(n);
-    memcpy(dst, b.data() + pos, n);
+    if (n) memcpy(dst, b.data() + pos, n);  // dst may be null for an empty block
     pos += n;
   }
   std::string str(size_t n) {
