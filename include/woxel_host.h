@@ -86,6 +86,10 @@ int wxh_renderer_set_sdf_on_gpu(WxhRenderer *r, int on);
 void wxh_renderer_last_sdf(const WxhRenderer *r, WxSdfInfo *out); /* device_ms == 0: the host sweep ran */
 /* fills the distances of a flat tree (taken before compute_sdf) on the GPU; WX_ERR_UNSUPPORTED: use wxh_vdb_compute_sdf */
 int wxh_flat_compute_sdf_gpu(WxhFlat *f, WxContext *ctx, WxSdfInfo *info);
+/* Frame dump after wx_capture_srgb (the reference's recorder pipes frames to ffmpeg, src/render/recorder.rs:67-105):
+ * rgb is height x width x 3 bytes.  Binary PPM (P6), or PNG (8-bit RGB, sRGB chunk). */
+int wxh_write_ppm(const char *path, const uint8_t *rgb, uint32_t width, uint32_t height);
+int wxh_write_png(const char *path, const uint8_t *rgb, uint32_t width, uint32_t height);
 WxContext *wxh_renderer_context(WxhRenderer *r);
 WxTree *wxh_renderer_tree(WxhRenderer *r);
 

@@ -45,6 +45,44 @@ def test_write_ppm_roundtrip(tmp_path):
     assert raw.startswith(b"P6\n7 5\n255\n") and raw[len(b"P6\n7 5\n255\n"):] == rgb.tobytes()
 
 
+def test_write_png_decodes_to_the_same_pixels(tmp_path):
+    """The host's PNG writer (frame_dump.cpp): checked chunk by chunk here and, when Pillow is importable, by a real decoder."""
+    import struct
+    import zlib
+    rng = np.random.default_rng(3)
+    for (h, w) in ((5, 7), (64, 129), (1, 1)):
+        rgb = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        p = tmp_path / f"f{h}x{w}.png"
+        W.write_png(str(p), rgb)
+        raw = p.read_bytes()
+        assert raw[:8] == b"\x89PNG\r\n\x1a\n"
+        pos, chunks = 8, []
+        while pos < len(raw):
+            n, typ = struct.unpack(">I4s", raw[pos:pos + 8])
+            data = raw[pos + 8:pos + 8 + n]
+            (crc,) = struct.unpack(">I", raw[pos + 8 + n:pos + 12 + n])
+            assert crc == zlib.crc32(typ + data)
+            chunks.append((typ, data))
+            pos += 12 + n
+        assert [c[0] for c in chunks] == [b"IHDR", b"sRGB", b"IDAT", b"IEND"]
+        assert struct.unpack(">IIBBBBB", chunks[0][1]) == (w, h, 8, 2, 0, 0, 0)
+        rows = np.frombuffer(zlib.decompress(chunks[2][1]), np.uint8).reshape(h, 1 + 3 * w)
+        assert not rows[:, 0].any() and np.array_equal(rows[:, 1:].reshape(h, w, 3), rgb)
+        try:
+            from PIL import Image
+        except ImportError:
+            continue
+        assert np.array_equal(np.asarray(Image.open(str(p)).convert("RGB")), rgb)
+
+
+def test_frame_dump_errors_are_statuses(tmp_path):
+    rgb = np.zeros((4, 4, 3), np.uint8)
+    with pytest.raises(W.WxError):
+        W.write_png(str(tmp_path / "no_such_dir" / "f.png"), rgb)
+    with pytest.raises(ValueError):
+        W.write_ppm(str(tmp_path / "f.ppm"), np.zeros((4, 4), np.uint8))
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("shape", [(256, 128, 1), (70, 30, 1), (101, 37, 3)])
 def test_capture_srgb_matches_oracle(gpu_ctx, shape):

@@ -10,7 +10,7 @@ There is no CPU fallback: rendering without the CUDA library or without a GPU ra
 from . import _ffi  # noqa: F401
 from .vdb import VDB345, VdbReader, FlatTree, VdbEndpoint, N3, N4, N5  # noqa: F401
 from .scene import Camera, Scene  # noqa: F401
-from .render import ComputeState, RenderMode, SunSettings, Renderer, Context, Tree, WxError, write_ppm  # noqa: F401
+from .render import ComputeState, RenderMode, SunSettings, Renderer, Context, Tree, WxError, write_ppm, write_png  # noqa: F401
 
 __all__ = ["VDB345", "VdbReader", "FlatTree", "VdbEndpoint", "N3", "N4", "N5", "Camera", "Scene", "ComputeState",
-           "RenderMode", "SunSettings", "Renderer", "Context", "Tree", "WxError", "write_ppm"]
+           "RenderMode", "SunSettings", "Renderer", "Context", "Tree", "WxError", "write_ppm", "write_png"]

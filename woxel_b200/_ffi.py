@@ -105,6 +105,8 @@ CUDA_API = {
 f3, u3, i3 = C.POINTER(C.c_float), C.POINTER(C.c_uint32), C.POINTER(C.c_int32)
 HOST_API = {
     "wxh_last_error": (C.c_char_p, []),
+    "wxh_write_ppm": (C.c_int, [C.c_char_p, vp, C.c_uint32, C.c_uint32]),
+    "wxh_write_png": (C.c_int, [C.c_char_p, vp, C.c_uint32, C.c_uint32]),
     "wxh_global_to_node": (C.c_int, [C.c_int, i3, i3]),
     "wxh_global_to_offset": (C.c_int64, [C.c_int, i3]),
     "wxh_offset_to_child": (C.c_int, [C.c_int, C.c_uint32, u3]),

@@ -245,5 +245,11 @@ extern "C" void wxh_renderer_last_sdf(const WxhRenderer* r, WxSdfInfo* out) { *o
 extern "C" int wxh_flat_compute_sdf_gpu(WxhFlat* f, WxContext* ctx, WxSdfInfo* info) {
   return guarded([&]() { return render::Renderer::compute_sdf_gpu(ctx, f->f, info) ? 0 : (int)WX_ERR_UNSUPPORTED; });
 }
+extern "C" int wxh_write_ppm(const char* path, const uint8_t* rgb, uint32_t width, uint32_t height) {
+  return guarded([&]() { return render::write_ppm(path, rgb, width, height), 0; });
+}
+extern "C" int wxh_write_png(const char* path, const uint8_t* rgb, uint32_t width, uint32_t height) {
+  return guarded([&]() { return render::write_png(path, rgb, width, height), 0; });
+}
 extern "C" WxContext* wxh_renderer_context(WxhRenderer* r) { return r->r.context(); }
 extern "C" WxTree* wxh_renderer_tree(WxhRenderer* r) { return r->r.tree(); }

@@ -78,4 +78,8 @@ class Renderer {
   WxTree* tree_ = nullptr;
 };
 
+// Frame dumps of the capture step (frame_dump.cpp): RGB8 [height][width][3] as binary PPM or PNG.  Throw std::exception on I/O errors.
+void write_ppm(const char* path, const uint8_t* rgb, uint32_t width, uint32_t height);
+void write_png(const char* path, const uint8_t* rgb, uint32_t width, uint32_t height);
+
 }  // namespace woxel::render

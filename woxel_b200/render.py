@@ -257,14 +257,24 @@ class Renderer:
         return out
 
 
+def _dump(fn_name: str, path: str, rgb: np.ndarray) -> None:
+    rgb = np.ascontiguousarray(rgb, np.uint8)
+    if rgb.ndim != 3 or rgb.shape[2] != 3:
+        raise ValueError("expected an RGB8 frame [H, W, 3]")
+    rc = getattr(_ffi.host_lib(), fn_name)(path.encode(), rgb.ctypes.data, rgb.shape[1], rgb.shape[0])
+    if rc != 0:
+        raise WxError(rc, _ffi.host_lib().wxh_last_error().decode())
+
+
 def write_ppm(path: str, rgb: np.ndarray) -> None:
     """Binary PPM (P6) of an RGB8 frame [H, W, 3]: the recorder's frame dump without ffmpeg (recorder.rs:67-105)."""
-    rgb = np.ascontiguousarray(rgb, np.uint8)
-    assert rgb.ndim == 3 and rgb.shape[2] == 3
-    with open(path, "wb") as f:
-        f.write(b"P6\n%d %d\n255\n" % (rgb.shape[1], rgb.shape[0]))
-        f.write(rgb.tobytes())
+    _dump("wxh_write_ppm", path, rgb)
+
+
+def write_png(path: str, rgb: np.ndarray) -> None:
+    """PNG (8-bit RGB, sRGB chunk) of an RGB8 frame [H, W, 3] (woxel_b200/host/frame_dump.cpp)."""
+    _dump("wxh_write_png", path, rgb)
 
 
 __all__ = ["WxError", "RenderMode", "SunSettings", "ComputeState", "Context", "Tree", "Renderer", "make_desc",
-           "VdbReader", "AOV_SPEC", "write_ppm"]
+           "VdbReader", "AOV_SPEC", "write_ppm", "write_png"]
