@@ -9,12 +9,16 @@ A "step" is one pass of the hot path over one batch of rays: every rank renders 
 (BASELINE.json config 3, the configuration the north-star target is quoted on).  Rank r looks from
 orbit camera r (camera 0 is config 3's camera; the sphere makes every orbit view the same workload),
 so per-GPU work is fixed as N grows ("scaling": "weak", BASELINE config 5's camera sharding).  For
-N > 1 every rank's kernel stores its pixels straight into one frame stack on GPU 0 through a CUDA-IPC
-peer mapping (the final store IS the NVLink gather; no separate collective on the data path).
+N > 1 every rank's frame is gathered in one frame stack on GPU 0 (mapped into the other processes through
+CUDA IPC) INSIDE the timed step: wx_render renders into the rank's own memory in row chunks and each finished
+chunk travels over NVLink by DMA while the next chunks render (no collective on the data path; NCCL only
+carries the barriers and the timing reductions).  WX_BENCH_GATHER=store selects the fused alternative, the
+kernel's own pixel stores going to the peer-mapped slot -- 30 % slower per step on 8 GPUs, see DESIGN.md section 5.
 
 Timing: W warm-up steps, then K steps between barrier+synchronize brackets; the device time of every
-step is taken with CUDA events on the launching stream, L2 is flushed (256 MiB write) before every
-timed step outside the event pair, and the per-step times are reduced with MAX over ranks.
+step is taken with CUDA events on the launching stream (N > 1: the library's own event pair around the
+whole wx_render call), L2 is flushed (256 MiB write) before every timed step outside the event pair, every
+rank sums its K step times and the job's time is the MAX over ranks.
 `e2e` goes through wx_render with HOST buffers: state H2D + kernel + RGBA D2H into pinned memory.
 
 The oracle (oracle/, a CPU restatement of the reference shader) is used here only for the reported
@@ -224,6 +228,9 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
 
+    sys.stdout.flush()
+    json_fd = os.dup(1)   # the ONE JSON line goes here; until then fd 1 is stderr (NCCL prints its version banner on fd 1)
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
     import __graft_entry__ as g
@@ -263,6 +270,17 @@ def main():
             h = (C.c_uint8 * 64).from_buffer_copy(objs[0])
             ctx.check(lib.wx_ipc_open(ctx._h, 0, h, C.byref(stack)))
     my_frame = stack.value + rank * frame_bytes
+    # How a rank's frame reaches the stack on GPU 0 when N > 1 (WX_BENCH_GATHER):
+    #   dma   (default) wx_render with the stack slot as destination: the frame is rendered into the rank's own memory in row
+    #         chunks and every finished chunk travels to GPU 0 by DMA over NVLink while the next chunks render;
+    #   store wx_render_device with the peer-mapped slot as output: the kernel's own 4-byte pixel stores cross NVLink
+    #         (measured 30 % slower per step on 8 GPUs: 16-byte row segments per warp make poor NVLink packets);
+    #   none  diagnostic only: the frame stays on the rank's GPU.
+    gather = os.environ.get("WX_BENCH_GATHER", "dma") if world > 1 else "none"
+    if world > 1 and gather == "none":
+        own = C.c_void_p()
+        ctx.check(lib.wx_device_alloc(ctx._h, 0, frame_bytes, C.byref(own)))
+        my_frame = own.value
 
     stream = torch.cuda.current_stream()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
@@ -273,13 +291,25 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
+    step_ms = []          # device time of every timed step of this rank
+    launches = [0]
+
     def step(timed_events=None):
-        flush.fill_(1)  # evict L2 (126 MB) between steps; outside the event pair
+        flush.fill_(1)  # evict L2 (126 MB) between steps; outside the timed region
+        if gather == "dma":
+            stream.synchronize()  # the library renders on its own streams: the flush must be over
+            ctx.render_to(tree, state, WIDTH, HEIGHT, my_frame)  # blocking; timed by the library's events on its launching stream
+            if timed_events is not None:
+                info = ctx.last_render_info()
+                step_ms.append(info.total_ms)  # kernels of all chunks + the DMA of the last chunk
+                launches[0] += info.launches
+            return
         if timed_events is not None:
             timed_events[0].record(stream)
         ctx.render_device(tree, state, WIDTH, HEIGHT, my_frame, stream=stream.cuda_stream)
         if timed_events is not None:
             timed_events[1].record(stream)
+            launches[0] += 1
 
     for _ in range(args.warmup):
         step()
@@ -295,24 +325,41 @@ def main():
         step(evs[k])
     sync_all()
     wall = time.perf_counter() - t_wall0
-    ms = torch.tensor([a.elapsed_time(b) for a, b in evs], dtype=torch.float64, device="cuda")
+    # device time of this rank's K steps; the job's time is the MAX over ranks (every rank renders K frames)
+    if gather != "dma":
+        step_ms.extend(a.elapsed_time(b) for a, b in evs)
+    ms = torch.tensor(step_ms, dtype=torch.float64, device="cuda")
+    assert ms.numel() == args.steps
+    total = ms.sum().reshape(1)
+    per_rank = [float(total.item()) / args.steps]
     if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)  # per-step max over ranks
-    ms = ms.cpu().numpy()
-    ms_per_step = float(ms.sum() / args.steps)
+        gathered = [torch.zeros_like(total) for _ in range(world)]
+        dist.all_gather(gathered, total)
+        per_rank = [float(t.item()) / args.steps for t in gathered]
+        dist.all_reduce(total, op=dist.ReduceOp.MAX)
+    ms_per_step = float(total.item() / args.steps)
     value = world * rays_per_frame / (ms_per_step * 1e-3) / 1e6
 
     # warm-L2 figure (no flush), for reference only
-    for _ in range(3):
-        ctx.render_device(tree, state, WIDTH, HEIGHT, my_frame, stream=stream.cuda_stream)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    sync_all()
-    e0.record(stream)
-    for _ in range(10):
-        ctx.render_device(tree, state, WIDTH, HEIGHT, my_frame, stream=stream.cuda_stream)
-    e1.record(stream)
-    sync_all()
-    warm_ms = torch.tensor([e0.elapsed_time(e1) / 10], dtype=torch.float64, device="cuda")
+    if gather == "dma":
+        sync_all()
+        w = 0.0
+        for _ in range(10):
+            ctx.render_to(tree, state, WIDTH, HEIGHT, my_frame)
+            w += ctx.last_render_info().total_ms
+        sync_all()
+        warm_ms = torch.tensor([w / 10], dtype=torch.float64, device="cuda")
+    else:
+        for _ in range(3):
+            ctx.render_device(tree, state, WIDTH, HEIGHT, my_frame, stream=stream.cuda_stream)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sync_all()
+        e0.record(stream)
+        for _ in range(10):
+            ctx.render_device(tree, state, WIDTH, HEIGHT, my_frame, stream=stream.cuda_stream)
+        e1.record(stream)
+        sync_all()
+        warm_ms = torch.tensor([e0.elapsed_time(e1) / 10], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(warm_ms, op=dist.ReduceOp.MAX)
     warm_ms = float(warm_ms.item())
@@ -385,22 +432,27 @@ def main():
             "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{what}, {WIDTH}x{HEIGHT}, render mode 0 (Gray, 1 hdda_ray/pixel), one frame per GPU per step "
-                                   f"(orbit camera = rank), frames stored into GPU0 over NVLink when N>1",
+                                   f"(orbit camera = rank)" + {"none": "", "dma": ", every frame gathered on GPU0 over NVLink (DMA of row chunks, "
+                                   "overlapped with the render of the next chunks, inside the timed region)", "store": ", every frame "
+                                   "stored into GPU0 over NVLink by the kernel itself"}[gather if world > 1 else "none"],
+                       "gather": gather,
                        "l2": "flushed (256 MiB fill) before every timed step; value_warm_l2 is the same loop without the flush",
                        "tree": {"n5": tree.info.n5, "n4": tree.info.n4, "n3": tree.info.n3, "leaf_bits": tree.info.leaf_bits,
                                 "device_MB": round(tree.info.device_bytes / 1e6, 1)},
                        "prep_s": prep},
             "value_warm_l2": round(world * rays_per_frame / (warm_ms * 1e-3) / 1e6, 1),
             "wall_ms_per_step_incl_flush": round(1e3 * wall / args.steps, 4),
+            "per_rank_ms_per_step": [round(x, 4) for x in per_rank],  # ms_per_step is their maximum
             "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": 256 * world, "d2h_bytes_per_step": frame_bytes * world,
                     "api": "wx_render (host state in, pinned host RGBA8 out), blocking; read-back pipelined over row chunks",
                     "steps": e2e_steps, "kernel_launches_per_step": int(e2e_info.launches),
                     "last_call_device_ms": {"kernels": round(e2e_info.kernel_ms, 4), "total_incl_readback": round(e2e_info.total_ms, 4)}},
-            "gpu_launches": args.steps * world,
+            "gpu_launches": launches[0] * world,  # raycast kernel launches inside the timed region (rank 0's count x ranks)
             "clocks": clocks, "roofline": roof, "cpu_baseline": cpu_baseline,
             "parity_vs_oracle_full_frame": parity, "frame_checksum": checksum,
         }
-        print(json.dumps(out))
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(out) + "\n").encode())
     if world > 1:
         dist.barrier()
         if rank != 0:

@@ -180,7 +180,10 @@ int wx_tree_build(WxContext *ctx, const WxTreeDesc *topo, WxTree **out, WxSdfInf
 
 /*
  * One frame per state (n_states > 1 = camera batch).  Blocking.  rgba_out is HOST memory,
- * n_states x height x width x 4 bytes (pinned memory makes the read-back faster; pageable works).
+ * n_states x height x width x 4 bytes (pinned memory makes the read-back faster; pageable works) -- or device memory
+ * of ANY GPU of the process's unified address space (another GPU's buffer, also one opened with wx_ipc_open): the frame
+ * is then delivered there by DMA, chunk by chunk while later chunks render; that is how one process per GPU gathers its
+ * frames on GPU 0 over NVLink (bench.py).  aov_out is host memory.
  * Pixels outside the reference's dispatch (x >= (W/8)*8 or y >= (H/4)*4, wgpu_context.rs:281) are
  * written as 0,0,0,0 like a freshly created texture.  With several devices the frames are split
  * by row bands / cameras, rendered concurrently and gathered on device 0 over NVLink.

@@ -741,7 +741,7 @@ static int render_distributed(WxContext* ctx, const WxTree* tree, const WxState*
       if (rc) return rc;
       *launches += l;
       WX_CUDA(ctx, cudaEventRecord(s.ev1, s.stream));
-      WX_CUDA(ctx, copy_own_bands(rgba_out, local, i, ndev, 0, n_states, 0, height, width, height, cudaMemcpyDeviceToHost, s.stream));
+      WX_CUDA(ctx, copy_own_bands(rgba_out, local, i, ndev, 0, n_states, 0, height, width, height, cudaMemcpyDefault, s.stream));
     } else {
       WX_CUDA(ctx, cudaEventRecord(s.fork, s.stream));
       cudaStream_t ks[3] = {s.stream, s.aux[0], s.aux[1]};
@@ -756,7 +756,7 @@ static int render_distributed(WxContext* ctx, const WxTree* tree, const WxState*
         *launches += l;
         WX_CUDA(ctx, cudaEventRecord(s.chunk_done[c_idx], st));
         WX_CUDA(ctx, cudaStreamWaitEvent(s.copy_stream, s.chunk_done[c_idx], 0));
-        WX_CUDA(ctx, copy_own_bands(rgba_out, local, i, ndev, ch.cam0, ch.cam1, ch.row0, ch.row1, width, height, cudaMemcpyDeviceToHost, s.copy_stream));
+        WX_CUDA(ctx, copy_own_bands(rgba_out, local, i, ndev, ch.cam0, ch.cam1, ch.row0, ch.row1, width, height, cudaMemcpyDefault, s.copy_stream));
       }
       for (int k = 0; k < 2; ++k) {
         WX_CUDA(ctx, cudaEventRecord(s.join[k], s.aux[k]));
@@ -883,7 +883,7 @@ extern "C" int wx_render(WxContext* ctx, const WxTree* tree, const WxState* stat
         WX_CUDA(ctx, cudaStreamWaitEvent(d0.copy_stream, d0.chunk_done[c], 0));
         const size_t off = ((size_t)ch.cam0 * height + ch.row0) * width * 4;
         const size_t bytes = ch.ncam > 1 || ch.row1 - ch.row0 == height ? (size_t)ch.ncam * height * width * 4 : (size_t)(ch.row1 - ch.row0) * width * 4;
-        WX_CUDA(ctx, cudaMemcpyAsync(rgba_out + off, ctx->fb.rgba + off, bytes, cudaMemcpyDeviceToHost, d0.copy_stream));
+        WX_CUDA(ctx, cudaMemcpyAsync(rgba_out + off, ctx->fb.rgba + off, bytes, cudaMemcpyDefault, d0.copy_stream));  // host, or any GPU's memory (UVA)
       }
       // join: the main stream waits for the other kernel streams (ev1 = all kernels done), then for the last copy
       for (int k = 0; k < 2; ++k) {
@@ -948,7 +948,7 @@ extern "C" int wx_render(WxContext* ctx, const WxTree* tree, const WxState* stat
     }
     WX_CUDA(ctx, cudaSetDevice(d0.id));
   }
-  if (!copied) WX_CUDA(ctx, cudaMemcpyAsync(rgba_out, ctx->fb.rgba, npix * 4, cudaMemcpyDeviceToHost, d0.stream));
+  if (!copied) WX_CUDA(ctx, cudaMemcpyAsync(rgba_out, ctx->fb.rgba, npix * 4, cudaMemcpyDefault, d0.stream));
   for (int k = 0; k < 8; ++k)
     if (host_aov[k]) WX_CUDA(ctx, cudaMemcpyAsync(host_aov[k], ctx->fb.aov[k], npix * aov_elem[k], cudaMemcpyDeviceToHost, d0.stream));
   WX_CUDA(ctx, cudaEventRecord(ctx->total1, d0.stream));

@@ -125,6 +125,13 @@ class Context:
                                              C.byref(a) if a is not None else None))
         return rgba, aovs
 
+    def render_to(self, tree: "Tree", states, width: int, height: int, dst_ptr: int) -> None:
+        """wx_render with a raw destination address: host memory or device memory of any GPU (also an IPC-mapped buffer of
+        another process's GPU).  Blocking; the frame is delivered chunk by chunk while later chunks render."""
+        states = list(states) if isinstance(states, (list, tuple)) else [states]
+        arr = (_ffi.WxState * len(states))(*states)
+        self.check(_ffi.cuda_lib().wx_render(self._h, tree._h, arr, len(states), width, height, C.c_void_p(dst_ptr), None))
+
     def compute_sdf(self, flat_or_desc, narrow_leaves: bool = False):
         """wx_compute_sdf: VDB345::compute_sdf (vdb345.rs:290-628) on the GPU for a flat tree (its tile / voxel
         distances are ignored on input).  Returns (tab5, tab4, tab3, WxSdfInfo) in the layout of FlatTree."""
