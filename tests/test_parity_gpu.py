@@ -255,6 +255,31 @@ def test_pipelined_readback_equals_single_launch(gpu_ctx):
         assert np.array_equal(plain[0], ref)
 
 
+@pytest.mark.parametrize("shape", [(1280, 824, 1), (200, 120, 3)])
+def test_wx_render_delivers_to_device_memory(gpu_ctx, shape):
+    """wx_render's destination may be device memory (how bench.py gathers the ranks' frames on GPU 0): the chunked,
+    pipelined delivery must put the same bytes there as into a host buffer."""
+    import ctypes as C
+    from woxel_b200 import _ffi
+    lib = _ffi.cuda_lib()
+    w, h, n = shape
+    tree = gpu_tree(gpu_ctx, "icosahedron")
+    cams = [scenes.CAMERAS["oblique_a"], scenes.CAMERAS["default"], scenes.CAMERAS["oblique_b"]]
+    states = [to_wx(scenes.state_for(*cams[k], w, h, mode=(3, 0, 4)[k])) for k in range(n)]
+    host, _ = gpu_ctx.render(tree, states, w, h)
+    nbytes = n * w * h * 4
+    dev = C.c_void_p()
+    gpu_ctx.check(lib.wx_device_alloc(gpu_ctx._h, 0, nbytes, C.byref(dev)))
+    try:
+        gpu_ctx.render_to(tree, states, w, h, dev.value)
+        back = np.empty((n, h, w, 4), np.uint8)
+        gpu_ctx.check(lib.wx_memcpy_d2h(gpu_ctx._h, 0, back.ctypes.data, dev, nbytes, None))
+        gpu_ctx.check(lib.wx_stream_synchronize(gpu_ctx._h, 0, None))
+        assert np.array_equal(back, host)
+    finally:
+        lib.wx_device_free(gpu_ctx._h, 0, dev)
+
+
 def _multi_contexts():
     """Device lists for the multi-device tests: 2 and all GPUs of the box; on a single-GPU box the same GPU listed 2 and
     3 times (wx_init gives every entry its own streams, frame and tree replica, so the sharding, the per-device
