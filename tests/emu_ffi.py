@@ -1,0 +1,63 @@
+"""ctypes view of tests/emu/libwx_emu.so -- TEST INFRASTRUCTURE: the device code of woxel_b200/csrc/wx_device.cuh compiled
+for the host (tests/emu/cuda_shim.h) and run lane by lane on the CPU over the tables wx_tree_upload would send to the GPU."""
+from __future__ import annotations
+
+import ctypes as C
+import functools
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+EMU_DIR = os.path.join(HERE, "emu")
+
+STAT_NAMES = ["rays", "warps", "lane_steps", "warp_steps", "root_blocks", "n5_blocks", "n4_blocks", "leaf_blocks", "generic_iters",
+              *[f"combo{i}" for i in range(8)], "lane_table_reads", "truncated"]
+
+
+@functools.lru_cache(maxsize=None)
+def lib() -> C.CDLL:
+    r = subprocess.run(["make", "-C", EMU_DIR], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"make -C tests/emu failed:\n{r.stdout}\n{r.stderr}")
+    L = C.CDLL(os.path.join(EMU_DIR, "libwx_emu.so"))
+    L.wxe_render.restype = C.c_int
+    L.wxe_render.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_int, C.c_uint32,
+                             C.c_void_p]
+    L.wxe_n_stats.restype = C.c_int
+    assert L.wxe_n_stats() == len(STAT_NAMES)
+    return L
+
+
+class Aov(C.Structure):  # == WxAov (include/woxel_b200.h)
+    _fields_ = [(k, C.c_void_p) for k in ("state", "voxel", "leaf", "level", "iters", "depth", "mask", "pos")]
+
+
+def render(desc, states, width: int, height: int, aov: bool = True, rcp_bump: int = 0, warp_w: int = 4, stats: bool = False):
+    """desc: WxTreeDesc (woxel_b200.render.make_desc); states: one or a list of 256-byte ComputeState objects.
+    Returns (rgba[n,H,W,4], aov dict of [n,...] arrays or None, stats dict or None)."""
+    if not isinstance(states, (list, tuple)):
+        states = [states]
+    n = len(states)
+    buf = (C.c_char * (256 * n))()
+    for i, s in enumerate(states):
+        b = bytes(s)
+        assert len(b) == 256
+        buf[256 * i:256 * (i + 1)] = b
+    rgba = np.zeros((n, height, width, 4), np.uint8)
+    out, a = None, None
+    if aov:
+        out = {
+            "state": np.zeros((n, height, width), np.uint8), "voxel": np.zeros((n, height, width, 3), np.int32),
+            "leaf": np.zeros((n, height, width), np.int32), "level": np.zeros((n, height, width), np.uint8),
+            "iters": np.zeros((n, height, width), np.uint32), "depth": np.zeros((n, height, width), np.float32),
+            "mask": np.zeros((n, height, width), np.uint8), "pos": np.zeros((n, height, width, 3), np.float32),
+        }
+        a = Aov(*[out[k].ctypes.data for k in ("state", "voxel", "leaf", "level", "iters", "depth", "mask", "pos")])
+    st = np.zeros(len(STAT_NAMES), np.uint64) if stats else None
+    rc = lib().wxe_render(C.addressof(desc), C.addressof(buf), n, width, height, rgba.ctypes.data, C.addressof(a) if a is not None else None,
+                          rcp_bump, warp_w, st.ctypes.data if st is not None else None)
+    if rc != 0:
+        raise RuntimeError(f"wxe_render failed: {rc}")
+    return rgba, out, (dict(zip(STAT_NAMES, (int(v) for v in st))) if st is not None else None)

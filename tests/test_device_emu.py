@@ -1,0 +1,105 @@
+"""The device code on the CPU: woxel_b200/csrc/wx_device.cuh compiled by g++ through tests/emu/cuda_shim.h (IEEE
+definitions of the intrinsics, MUFU.RCP = 1/v bumped by -1 / 0 / +1 ulp) and run lane by lane over the tables
+wx_tree_upload builds, against the oracle.  No GPU: this is what keeps the value-exact rewrites of the fast march
+(round-down-add floor, division-free modulo, cursor, root cells, byte leaves, predicated nudge) pinned to the oracle in the
+CPU suite, and what lets a change to the march be checked before any GPU time is spent.  The GPU parity tests proper are
+tests/test_parity_gpu.py."""
+import numpy as np
+import pytest
+
+import emu_ffi as E
+import scenes
+
+
+def _bits_nan_canonical(a):
+    b = np.ascontiguousarray(a, np.float32).view(np.uint32).copy()
+    b[np.isnan(a)] = 0x7FC00000
+    return b
+
+
+def check(name, st, w, h, rcp_bump=0):
+    s = scenes.get_scene(name)
+    rgba, aov, _ = E.render(s.desc(), st, w, h, aov=True, rcp_bump=rcp_bump)
+    rgba, aov = rgba[0], {k: v[0] for k, v in aov.items()}
+    ref_rgba, ref_aov, stats = s.gpu.render(st, w, h)
+    dw, dh = (w // 8) * 8, (h // 4) * 4
+    assert not rgba[dh:].any() and not rgba[:, dw:].any()
+    assert np.array_equal(rgba, ref_rgba), (name, int((rgba != ref_rgba).any(-1).sum()))
+    for k in ("state", "voxel", "leaf", "level", "iters", "mask"):
+        assert np.array_equal(aov[k][:dh, :dw], ref_aov[k][:dh, :dw]), (name, k)
+    for k in ("depth", "pos"):
+        assert np.array_equal(_bits_nan_canonical(aov[k][:dh, :dw]), _bits_nan_canonical(ref_aov[k][:dh, :dw])), (name, k)
+    return stats
+
+
+@pytest.mark.parametrize("name", ["cube", "icosahedron"])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3, 4])
+def test_assets_all_modes(name, mode):
+    eye, target = scenes.CAMERAS["oblique_a" if mode % 2 else "default"]
+    st = scenes.state_for(eye, target, 240, 136, mode=mode, show_grid=(1, 1, 1) if mode < 3 else (0, 0, 0))
+    check(name, st, 240, 136)
+
+
+@pytest.mark.parametrize("bump", [-1, 1])
+@pytest.mark.parametrize("name", ["cube", "icosahedron", "small_sphere"])
+def test_any_allowed_reciprocal_gives_the_same_frame(name, bump):
+    """MUFU.RCP is specified to 1 ulp: the march must not depend on which value comes back."""
+    eye, target = scenes.CAMERAS["oblique_b"] if name != "small_sphere" else ((90.5, 70.5, -120.5), (0.0, 0.0, 0.0))
+    st = scenes.state_for(eye, target, 320, 180, mode=3)
+    check(name, st, 320, 180, rcp_bump=bump)
+
+
+@pytest.mark.parametrize("name,eye,target", [
+    ("small_sphere", (0.5, 0.5, -200.5), (0.5, 0.5, 0.5)),
+    ("offcentre_sphere", (300.5, 140.5, -400.5), (300.0, 140.0, -260.0)),
+    ("scattered", (10.5, 20.5, -900.5), (0.0, 0.0, 0.0)),
+    ("single_voxel", (5.5, 6.5, -20.5), (5.5, 6.5, 7.5)),
+    ("beyond_bounds", (0.5, 0.5, -150.5), (0.5, 0.5, 0.5)),
+    ("beyond_bounds", (4000.5, 30.5, -150.5), (4100.0, 3.0, 3.0)),
+    ("slab", (0.5, 4.0, -300.5), (0.5, 4.0, 0.5)),          # rays in the slab's top plane: exact ties
+    ("long_slab", (-900.5, 4.0005, 0.5), (0.5, 4.0005, 0.5)),  # grazing rays that run out of steps (state 2)
+    ("active_tiles", (90.5, 70.5, -120.5), (0.0, 0.0, 0.0)),
+    ("empty_leaf", (90.5, 70.5, -120.5), (0.0, 0.0, 0.0)),
+])
+@pytest.mark.parametrize("mode", [0, 4])
+def test_edge_scenes(name, eye, target, mode):
+    st = scenes.state_for(eye, target, 200, 100, mode=mode)
+    check(name, st, 200, 100)
+
+
+def test_axis_aligned_and_outside_cameras():
+    """Direction components that are exactly 0 (1/dir = inf: the exact march) and an eye outside the +-4096 world."""
+    s = "small_sphere"
+    check(s, scenes.state_for((0.0, 0.0, -200.0), (0.0, 0.0, 0.0), 64, 64, mode=0), 64, 64)  # centre ray along +z... with the 0.001 offset
+    check(s, scenes.state_for((0.5, 0.5, -5000.5), (0.5, 0.5, 0.5), 64, 32, mode=3), 64, 32)
+    check(s, scenes.state_for((4095.9, 0.5, -200.5), (0.5, 0.5, 0.5), 64, 32, mode=1), 64, 32)
+
+
+def test_ragged_frame_sizes():
+    for w, h in ((8, 4), (13, 7), (100, 50), (7, 3)):
+        check("cube", scenes.state_for(*scenes.CAMERAS["default"], w, h, mode=0), w, h)
+
+
+def test_camera_batch_mixed_modes():
+    s = scenes.get_scene("icosahedron")
+    sts = [scenes.state_for(*scenes.CAMERAS[c], 96, 64, mode=m) for c, m in (("default", 0), ("oblique_a", 3), ("oblique_b", 4), ("default", 2))]
+    rgba, aov, _ = E.render(s.desc(), sts, 96, 64)
+    for i, st in enumerate(sts):
+        ref_rgba, ref_aov, _ = s.gpu.render(st, 96, 64)
+        assert np.array_equal(rgba[i], ref_rgba), i
+        assert np.array_equal(aov["iters"][i], ref_aov["iters"]), i
+
+
+def test_warp_statistics_are_consistent():
+    """The lockstep replay of 4x8-pixel warps: lane steps equal the lookups the AOVs imply, and the level counts add up."""
+    s = scenes.get_scene("cube")
+    st2 = scenes.state_for(*scenes.CAMERAS["oblique_a"], 320, 176, mode=0)
+    _, aov, stats = E.render(s.desc(), st2, 320, 176, stats=True)
+    assert stats["rays"] == 320 * 176 and stats["truncated"] == 0
+    # every ray's lookups: one per loop iteration entered = iters + 1 for rays that ended inside the loop, iters for maxed ones
+    it = aov["iters"][0].astype(np.int64)
+    ended = aov["state"][0] != 2
+    assert stats["lane_steps"] == int((it + ended).sum())
+    assert sum(stats[f"combo{i}"] for i in range(8)) == stats["warp_steps"]
+    assert stats["generic_iters"] <= stats["n5_blocks"] + stats["n4_blocks"] + stats["leaf_blocks"]
+    assert stats["warp_steps"] * 32 >= stats["lane_steps"]

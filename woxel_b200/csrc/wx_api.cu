@@ -17,6 +17,7 @@
 
 #include "wx_device.cuh"
 #include "wx_internal.h"
+#include "wx_pack.h"
 
 using namespace wx;
 
@@ -227,97 +228,16 @@ extern "C" int wx_device_count(const WxContext* ctx) { return ctx ? (int)ctx->de
 // ---------------------------------------------------------------------------------------------
 // Tree packing: WxTreeDesc (reference order: masks + per-slot u32) -> entry tables + leaf bricks
 // ---------------------------------------------------------------------------------------------
-template <class F>
-static void parallel_for(size_t n, F&& f) {
-  unsigned hw = std::thread::hardware_concurrency();
-  size_t nt = std::min<size_t>(hw ? hw : 1, std::max<size_t>(1, n / 64));
-  if (nt <= 1) {
-    for (size_t i = 0; i < n; ++i) f(i);
-    return;
-  }
-  std::atomic<size_t> next{0};
-  std::vector<std::thread> th;
-  auto body = [&]() {
-    for (;;) {
-      size_t b = next.fetch_add(256);
-      if (b >= n) break;
-      size_t e = std::min(n, b + 256);
-      for (size_t i = b; i < e; ++i) f(i);
-    }
-  };
-  for (size_t t = 1; t < nt; ++t) th.emplace_back(body);
-  body();
-  for (auto& t : th) t.join();
-}
-
-static inline bool bit(const uint64_t* m, size_t i) { return (m[i >> 6] >> (i & 63)) & 1ull; }
-
-static inline uint32_t float_bits(float f) {
-  uint32_t u;
-  memcpy(&u, &f, 4);
-  return u;
-}
-
-// One internal level.  Returns 0, or a negative status; *max_dist receives the largest tile distance.
-// A tile entry is the f32 bit pattern of f32(dist) * cell, the `size` of raycast.comp.wgsl:104.
-static int pack_internal(uint32_t n_nodes, uint32_t slots, float cell, const uint64_t* kids, const uint64_t* vals,
-                         const uint32_t* tab, uint32_t n_children, std::vector<uint32_t>& out, uint32_t* max_dist) {
-  out.assign((size_t)n_nodes * slots, 0u);
-  std::atomic<int> status{0};
-  std::atomic<uint32_t> mx{0};
-  parallel_for(n_nodes, [&](size_t node) {
-    const uint64_t* k = kids + node * (slots / 64);
-    const uint64_t* v = vals + node * (slots / 64);
-    const uint32_t* t = tab + node * slots;
-    uint32_t* o = out.data() + node * slots;
-    uint32_t local_max = 0;
-    for (uint32_t s = 0; s < slots; ++s) {
-      if (bit(v, s)) {
-        o[s] = 0u;  // active tile: a hit, whatever the child bit says (raycast.comp.wgsl:431-433)
-      } else if (bit(k, s)) {
-        if (t[s] >= n_children) {
-          status.store(WX_ERR_BAD_TREE);
-          return;
-        }
-        o[s] = kChildFlag | t[s];
-      } else {
-        if (t[s] & kChildFlag) {
-          status.store(WX_ERR_UNSUPPORTED);
-          return;
-        }
-        o[s] = float_bits((float)t[s] * cell);
-        local_max = std::max(local_max, t[s]);
-      }
-    }
-    uint32_t cur = mx.load();
-    while (local_max > cur && !mx.compare_exchange_weak(cur, local_max)) {
-    }
-  });
-  *max_dist = mx.load();
-  return status.load();
-}
-
 // Host-side part of a device tree: biased origins, root cells, limits, info.
 static WxTree* new_tree(WxContext* ctx, const WxTreeDesc* d, uint32_t leaf_bits, uint32_t max5, uint32_t max4, uint32_t max3v) {
   WxTree* t = new (std::nothrow) WxTree();
   if (!t) return nullptr;
   t->ctx = ctx;
-  t->origins.resize(d->n5);
-  for (uint32_t i = 0; i < d->n5; ++i)  // biased like the voxel coordinates the kernel derives from float bits (modular)
-    t->origins[i] = make_int4((int)((uint32_t)d->origins[3 * i] + kBias), (int)((uint32_t)d->origins[3 * i + 1] + kBias),
-                              (int)((uint32_t)d->origins[3 * i + 2] + kBias), 0);
-  for (int16_t& v : t->root_grid) v = (int16_t)kRootNone;
-  for (uint32_t i = d->n5; i-- > 0;) {  // descending: the first of equal origins wins, as in the reference's scan
-    const int32_t* o = d->origins + 3 * i;
-    const int64_t cx = ((int64_t)o[0] >> 12) + 2, cy = ((int64_t)o[1] >> 12) + 2, cz = ((int64_t)o[2] >> 12) + 2;
-    if ((o[0] & 4095) || (o[1] & 4095) || (o[2] & 4095)) continue;  // an unaligned origin never equals (pos >> 12) << 12
-    if (cx < 0 || cx > 3 || cy < 0 || cy > 3 || cz < 0 || cz > 3) continue;
-    const bool beyond = cx < 1 || cx > 2 || cy < 1 || cy > 2 || cz < 1 || cz > 2;  // origin component outside [-4096, 0]
-    t->root_grid[cx * 16 + cy * 4 + cz] = i <= (uint32_t)kRootIndexMask ? (int16_t)(i | (beyond ? kRootBeyond : 0)) : (int16_t)kRootScan;
-  }
+  bias_origins(d->n5, d->origins, t->origins);
+  build_root_grid(d->n5, d->origins, t->root_grid);
   t->leaf_shift = leaf_bits == 8 ? 9 : 11;
   // the fast march needs byte leaves and every step size below 2^20 (wx_device.cuh); anything else takes the exact march
-  t->fast_ok = leaf_bits == 8 && (double)max5 * 128.0 < (double)kFastMaxSize && (double)max4 * 8.0 < (double)kFastMaxSize && (double)max3v < (double)kFastMaxSize;
+  t->fast_ok = fast_march_ok(leaf_bits, max5, max4, max3v);
   t->info.n5 = d->n5, t->info.n4 = d->n4, t->info.n3 = d->n3;
   t->info.leaf_bits = leaf_bits;
   t->info.max_dist[0] = max5, t->info.max_dist[1] = max4, t->info.max_dist[2] = max3v;
@@ -347,33 +267,8 @@ extern "C" int wx_tree_upload(WxContext* ctx, const WxTreeDesc* d, WxTree** out)
   if (rc) return fail(ctx, rc, "wx_tree_upload: N4 table (child index out of range or distance >= 2^31)");
 
   // leaf distance width: the largest inactive-voxel distance decides (one byte per voxel, else u32)
-  const uint8_t* t8 = (const uint8_t*)d->tab3;
-  const uint32_t* t32 = (const uint32_t*)d->tab3;
-  const bool narrow = d->tab3_elem_bytes == 1;
-  std::atomic<uint32_t> mx3{0};
-  parallel_for(d->n3, [&](size_t leaf) {
-    const uint64_t* v = d->vals3 + leaf * 8;
-    uint32_t local_max = 0;
-    for (uint32_t s = 0; s < 512; ++s)
-      if (!bit(v, s)) local_max = std::max(local_max, narrow ? (uint32_t)t8[leaf * 512 + s] : t32[leaf * 512 + s]);
-    uint32_t cur = mx3.load();
-    while (local_max > cur && !mx3.compare_exchange_weak(cur, local_max)) {
-    }
-  });
-  const uint32_t max3v = mx3.load();
-  const uint32_t leaf_bits = max3v <= 255 ? 8 : 32;
-  const uint32_t leaf_shift = leaf_bits == 8 ? 9 : 11;
-  l3.assign((size_t)d->n3 << leaf_shift, 0u);
-  parallel_for(d->n3, [&](size_t leaf) {
-    const uint64_t* v = d->vals3 + leaf * 8;
-    uint8_t* o8 = l3.data() + (leaf << leaf_shift);
-    uint32_t* o32 = reinterpret_cast<uint32_t*>(o8);
-    for (uint32_t s = 0; s < 512; ++s) {
-      const uint32_t dist = bit(v, s) ? 0u : (narrow ? (uint32_t)t8[leaf * 512 + s] : t32[leaf * 512 + s]);
-      if (leaf_bits == 8) o8[s] = (uint8_t)dist;
-      else o32[s] = dist;
-    }
-  });
+  uint32_t max3v = 0;
+  const uint32_t leaf_bits = pack_leaves(d->n3, d->vals3, d->tab3, d->tab3_elem_bytes, l3, &max3v);
 
   WxTree* t = new_tree(ctx, d, leaf_bits, max5, max4, max3v);
   if (!t) return fail(ctx, WX_ERR_OUT_OF_MEMORY, "wx_tree_upload: host allocation");
@@ -561,14 +456,8 @@ static int launch_on(WxContext* ctx, int dev_i, const WxTree* tree, const WxStat
   const TreeOnDevice& o = tree->on[dev_i];
   RenderParams P;
   memset(&P, 0, sizeof(P));
-  P.tree.e5 = o.e5, P.tree.e4 = o.e4, P.tree.l3 = o.l3, P.tree.origins_g = o.origins;
-  // a child entry keeps its flag bit: node = adj + entry * node_bytes, adj = base - 2^31 * node_bytes
-  P.tree.e4_adj = reinterpret_cast<const char*>(o.e4) - ((uint64_t)kChildFlag << 14);
-  P.tree.l3_adj = reinterpret_cast<const char*>(o.l3) - ((uint64_t)kChildFlag << tree->leaf_shift);
-  P.tree.n5 = tree->info.n5, P.tree.n4 = tree->info.n4, P.tree.n3 = tree->info.n3;
-  P.tree.leaf_shift = tree->leaf_shift;
-  P.tree.fast_ok = tree->fast_ok ? 1u : 0u;
-  memcpy(P.tree.root_grid, tree->root_grid, sizeof(P.tree.root_grid));
+  fill_dev_tree(P.tree, o.e5, o.e4, o.l3, o.origins, tree->info.n5, tree->info.n4, tree->info.n3, tree->leaf_shift, tree->fast_ok,
+                tree->root_grid);
   P.n_states = n_states;
   P.width = width, P.height = height;
   P.rgba = reinterpret_cast<uchar4*>(rgba_dev);

@@ -131,11 +131,15 @@ __device__ __forceinline__ V3 sign11(V3 d) {
 // add is done with scalar FADDs, which ptxas leaves alone.
 // ---------------------------------------------------------------------------------------------
 typedef unsigned long long f32x2;
+#ifndef WX_HOST_EMU
 __device__ __forceinline__ f32x2 pk(float lo, float hi) {
   f32x2 r;
   asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
   return r;
 }
+#else  // tests/emu: this header compiled by the host compiler; the PTX-only primitives come from tests/emu/cuda_shim.h
+__device__ __forceinline__ f32x2 pk(float lo, float hi) { return (f32x2)__float_as_uint(lo) | ((f32x2)__float_as_uint(hi) << 32); }
+#endif
 __device__ __forceinline__ f32x2 bc(float v) { return pk(v, v); }
 __device__ __forceinline__ float lo(f32x2 v) { return __uint_as_float((uint32_t)v); }
 __device__ __forceinline__ float hi(f32x2 v) { return __uint_as_float((uint32_t)(v >> 32)); }
@@ -172,11 +176,15 @@ __device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) { return pk(__fsub_rn(lo
 __device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { return pk(__fmaf_rn(lo(a), lo(b), lo(c)), __fmaf_rn(hi(a), hi(b), hi(c))); }
 __device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { return pk(__fmul_rn(lo(a), lo(b)), __fmul_rn(hi(a), hi(b))); }
 #endif
+#ifndef WX_HOST_EMU
 __device__ __forceinline__ float rcp_approx(float v) {  // MUFU.RCP, <= 1 ulp
   float r;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
   return r;
 }
+#else
+__device__ __forceinline__ float rcp_approx(float v) { return wx_emu_rcp(v); }  // 1/v, bumped by the ulps the test asks for
+#endif
 
 // ---------------------------------------------------------------------------------------------
 // Tree cursor: the path to the voxel visited last.
@@ -201,9 +209,13 @@ __device__ __forceinline__ uint32_t cursor_level(uint32_t dbits) {
 }
 
 __device__ __forceinline__ float u32_to_float(uint32_t v) {  // I2FP (alu pipe); a u8/u16 source would go to the XU pipe
+#ifndef WX_HOST_EMU
   float f;
   asm("cvt.rn.f32.u32 %0, %1;" : "=f"(f) : "r"(v));
   return f;
+#else
+  return (float)v;
+#endif
 }
 
 // Walk down from the level the cursor is still valid for: dv >= 128 starts at the N5 table c.q5,
@@ -308,6 +320,9 @@ struct HitOut {
 };
 
 constexpr uint32_t kMaxRaySteps = 1000u;
+#ifndef WX_EMU_STEP
+#define WX_EMU_STEP(dv0, dbits) ((void)(dv0))  // tests/emu records the level walk of every step here; nothing on the device
+#endif
 #ifndef WX_UNROLL
 #define WX_UNROLL 2  // two steps per loop trip: the cursor's last-voxel registers alternate instead of being copied
 #endif
@@ -416,7 +431,9 @@ static __device__ __noinline__ HitOut march_exact(const DevTree& T, V3 src, V3 d
 //  (5) p += 4e-4 * step * mask adds exactly +-4e-4 or +-0: a predicated add.
 //  (6) the bounds test can only succeed where lookup() says so (see Cursor).
 __device__ __forceinline__ float keep(float v) {  // the value stays in its register (no rematerialisation in the loop)
+#ifndef WX_HOST_EMU
   asm volatile("" : "+f"(v));
+#endif
   return v;
 }
 
@@ -452,9 +469,11 @@ struct FastRay {
     c.lx = x, c.ly = y, c.lz = z;
     // lookup L(pos): from the root only when the N5 changed, else from the deepest cached node
     bool beyond = false;
+    const uint32_t dv0 = dv;
     if (dv >= 4096u) beyond = enter_root(T, c, dv, x, y, z);
     if (dv < 4096u) size = descend<false>(T, c, dv, x, y, z);
     else size = 4096.f;  // no N5 here: dist 1 at level 0 (:411)
+    WX_EMU_STEP(dv0, c.dbits);
     if (size == 0.f) return true;
     if (beyond) {  // the only places where the bounds test of :100-103 can succeed (see Cursor)
       if (out_of_bounds(lo(pxy), hi(pxy), pz)) return true;
@@ -655,6 +674,77 @@ __device__ __forceinline__ uint32_t unorm8(float c) {
   if (c != c) return 0u;
   c = fminf(fmaxf(c, 0.f), 1.f);
   return (uint32_t)__float2int_rn(c * 255.0f);
+}
+
+// ---------------------------------------------------------------------------------------------
+// cp_main (raycast.comp.wgsl:60-68) for one pixel.  Lives here (not next to the kernels) so that the host emulation of
+// tests/emu compiles exactly the code the kernels run.
+// ---------------------------------------------------------------------------------------------
+struct PixelRef {
+  uint32_t x, y, cam;
+  bool in_frame;    // a pixel of the frame this launch owns
+  bool dispatched;  // inside the reference's dispatch (wgpu_context.rs:281)
+};
+
+template <int MODE, bool AOV>
+__device__ __forceinline__ void shade_and_store(const RenderParams& P, const PixelRef& q, const HitOut& hit, V3 dir) {
+  const WxState& s = (P.n_states == 1) ? P.s0 : P.states[q.cam];
+  const size_t pix = ((size_t)q.cam * P.height + q.y) * P.width + q.x;
+  const V3 col = shade<MODE>(P.tree, s, hit, dir);
+  P.rgba[pix] = make_uchar4((unsigned char)unorm8(col.x), (unsigned char)unorm8(col.y), (unsigned char)unorm8(col.z), 255);
+  if (AOV) {
+    const AovPtrs& a = P.aov;
+    if (a.state) a.state[pix] = (uint8_t)hit.state;
+    if (a.voxel) {
+      a.voxel[3 * pix + 0] = __float2int_rd(hit.p.x);
+      a.voxel[3 * pix + 1] = __float2int_rd(hit.p.y);
+      a.voxel[3 * pix + 2] = __float2int_rd(hit.p.z);
+    }
+    if (a.leaf) a.leaf[pix] = hit.level == 3u ? (int32_t)hit.n3 : -1;
+    if (a.level) a.level[pix] = (uint8_t)hit.level;
+    if (a.iters) a.iters[pix] = hit.i;
+    if (a.depth) {
+      const V3 d = hit.p - V3{s.eye[0], s.eye[1], s.eye[2]};
+      a.depth[pix] = sqrtf(dot3(d, d));
+    }
+    if (a.mask) a.mask[pix] = (uint8_t)hit.mask;
+    if (a.pos) a.pos[3 * pix + 0] = hit.p.x, a.pos[3 * pix + 1] = hit.p.y, a.pos[3 * pix + 2] = hit.p.z;
+  }
+}
+
+// cp_main (:60-68) for one pixel: ray generation, hdda_ray, ray_trace, store.
+template <int MODE, bool AOV>
+__device__ __forceinline__ void render_pixel(const RenderParams& P, const PixelRef& q) {
+  if (!q.in_frame) return;
+  if (!q.dispatched) {  // never dispatched by the reference: zero-initialised texel (and zeroed AOVs)
+    const size_t pix = ((size_t)q.cam * P.height + q.y) * P.width + q.x;
+    P.rgba[pix] = make_uchar4(0, 0, 0, 0);
+    if (AOV) {
+      const AovPtrs& a = P.aov;
+      if (a.state) a.state[pix] = 0;
+      if (a.voxel) a.voxel[3 * pix + 0] = a.voxel[3 * pix + 1] = a.voxel[3 * pix + 2] = 0;
+      if (a.leaf) a.leaf[pix] = 0;
+      if (a.level) a.level[pix] = 0;
+      if (a.iters) a.iters[pix] = 0;
+      if (a.depth) a.depth[pix] = 0.f;
+      if (a.mask) a.mask[pix] = 0;
+      if (a.pos) a.pos[3 * pix + 0] = a.pos[3 * pix + 1] = a.pos[3 * pix + 2] = 0.f;
+    }
+    return;
+  }
+  // the ray basis: from the constant bank for a single state (the usual frame), else from the batch in global memory
+  V3 u, mv, wp, eye;
+  if (P.n_states == 1) {
+    u = V3{P.s0.u[0], P.s0.u[1], P.s0.u[2]}, mv = V3{P.s0.mv[0], P.s0.mv[1], P.s0.mv[2]};
+    wp = V3{P.s0.wp[0], P.s0.wp[1], P.s0.wp[2]}, eye = V3{P.s0.eye[0], P.s0.eye[1], P.s0.eye[2]};
+  } else {
+    const float4* s4 = reinterpret_cast<const float4*>(P.states + q.cam);  // eye, u, mv, wp are the float4s 8..11 of the state
+    const float4 e = __ldg(s4 + 8), a = __ldg(s4 + 9), b = __ldg(s4 + 10), c = __ldg(s4 + 11);
+    eye = V3{e.x, e.y, e.z}, u = V3{a.x, a.y, a.z}, mv = V3{b.x, b.y, b.z}, wp = V3{c.x, c.y, c.z};
+  }
+  const float px = (float)q.x + 0.001f, py = (float)q.y + 0.001f;
+  const V3 dir = normalize3((px * u + py * mv) + wp);
+  shade_and_store<MODE, AOV>(P, q, hdda_ray(P.tree, eye, dir), dir);
 }
 
 }  // namespace wx

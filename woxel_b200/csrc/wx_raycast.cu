@@ -30,73 +30,6 @@ constexpr int kThreads = 32 * WX_CTA_WARPS;
 #define WX_MIN_BLOCKS (36 / WX_CTA_WARPS)  // resident CTAs per SM the register budget is capped for (36 warps -> 56 registers)
 #endif
 
-struct PixelRef {
-  uint32_t x, y, cam;
-  bool in_frame;    // a pixel of the frame this launch owns
-  bool dispatched;  // inside the reference's dispatch (wgpu_context.rs:281)
-};
-
-template <int MODE, bool AOV>
-__device__ __forceinline__ void shade_and_store(const RenderParams& P, const PixelRef& q, const HitOut& hit, V3 dir) {
-  const WxState& s = (P.n_states == 1) ? P.s0 : P.states[q.cam];
-  const size_t pix = ((size_t)q.cam * P.height + q.y) * P.width + q.x;
-  const V3 col = shade<MODE>(P.tree, s, hit, dir);
-  P.rgba[pix] = make_uchar4((unsigned char)unorm8(col.x), (unsigned char)unorm8(col.y), (unsigned char)unorm8(col.z), 255);
-  if (AOV) {
-    const AovPtrs& a = P.aov;
-    if (a.state) a.state[pix] = (uint8_t)hit.state;
-    if (a.voxel) {
-      a.voxel[3 * pix + 0] = __float2int_rd(hit.p.x);
-      a.voxel[3 * pix + 1] = __float2int_rd(hit.p.y);
-      a.voxel[3 * pix + 2] = __float2int_rd(hit.p.z);
-    }
-    if (a.leaf) a.leaf[pix] = hit.level == 3u ? (int32_t)hit.n3 : -1;
-    if (a.level) a.level[pix] = (uint8_t)hit.level;
-    if (a.iters) a.iters[pix] = hit.i;
-    if (a.depth) {
-      const V3 d = hit.p - V3{s.eye[0], s.eye[1], s.eye[2]};
-      a.depth[pix] = sqrtf(dot3(d, d));
-    }
-    if (a.mask) a.mask[pix] = (uint8_t)hit.mask;
-    if (a.pos) a.pos[3 * pix + 0] = hit.p.x, a.pos[3 * pix + 1] = hit.p.y, a.pos[3 * pix + 2] = hit.p.z;
-  }
-}
-
-// cp_main (:60-68) for one pixel: ray generation, hdda_ray, ray_trace, store.
-template <int MODE, bool AOV>
-__device__ __forceinline__ void render_pixel(const RenderParams& P, const PixelRef& q) {
-  if (!q.in_frame) return;
-  if (!q.dispatched) {  // never dispatched by the reference: zero-initialised texel (and zeroed AOVs)
-    const size_t pix = ((size_t)q.cam * P.height + q.y) * P.width + q.x;
-    P.rgba[pix] = make_uchar4(0, 0, 0, 0);
-    if (AOV) {
-      const AovPtrs& a = P.aov;
-      if (a.state) a.state[pix] = 0;
-      if (a.voxel) a.voxel[3 * pix + 0] = a.voxel[3 * pix + 1] = a.voxel[3 * pix + 2] = 0;
-      if (a.leaf) a.leaf[pix] = 0;
-      if (a.level) a.level[pix] = 0;
-      if (a.iters) a.iters[pix] = 0;
-      if (a.depth) a.depth[pix] = 0.f;
-      if (a.mask) a.mask[pix] = 0;
-      if (a.pos) a.pos[3 * pix + 0] = a.pos[3 * pix + 1] = a.pos[3 * pix + 2] = 0.f;
-    }
-    return;
-  }
-  // the ray basis: from the constant bank for a single state (the usual frame), else from the batch in global memory
-  V3 u, mv, wp, eye;
-  if (P.n_states == 1) {
-    u = V3{P.s0.u[0], P.s0.u[1], P.s0.u[2]}, mv = V3{P.s0.mv[0], P.s0.mv[1], P.s0.mv[2]};
-    wp = V3{P.s0.wp[0], P.s0.wp[1], P.s0.wp[2]}, eye = V3{P.s0.eye[0], P.s0.eye[1], P.s0.eye[2]};
-  } else {
-    const float4* s4 = reinterpret_cast<const float4*>(P.states + q.cam);  // eye, u, mv, wp are the float4s 8..11 of the state
-    const float4 e = __ldg(s4 + 8), a = __ldg(s4 + 9), b = __ldg(s4 + 10), c = __ldg(s4 + 11);
-    eye = V3{e.x, e.y, e.z}, u = V3{a.x, a.y, a.z}, mv = V3{b.x, b.y, b.z}, wp = V3{c.x, c.y, c.z};
-  }
-  const float px = (float)q.x + 0.001f, py = (float)q.y + 0.001f;
-  const V3 dir = normalize3((px * u + py * mv) + wp);
-  shade_and_store<MODE, AOV>(P, q, hdda_ray(P.tree, eye, dir), dir);
-}
-
 // Tiled kernel: one thread per pixel of the grid, a warp per 8x4 tile, a CTA per 2x2 tiles.
 template <int MODE, bool AOV>
 __global__ void __launch_bounds__(kThreads, WX_MIN_BLOCKS) raycast_kernel(const __grid_constant__ RenderParams P) {
