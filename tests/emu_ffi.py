@@ -18,10 +18,13 @@ STAT_NAMES = ["rays", "warps", "lane_steps", "warp_steps", "root_blocks", "n5_bl
 
 @functools.lru_cache(maxsize=None)
 def lib() -> C.CDLL:
-    r = subprocess.run(["make", "-C", EMU_DIR], capture_output=True, text=True)
+    # WX_EMU_EXTRA="-DWX_..." builds (and loads) the emulation of a build-time variant of the kernel (measurement knobs)
+    extra = os.environ.get("WX_EMU_EXTRA", "")
+    out = "libwx_emu.so" if not extra else "libwx_emu_" + "".join(ch if ch.isalnum() else "_" for ch in extra) + ".so"
+    r = subprocess.run(["make", "-C", EMU_DIR, f"EXTRA={extra}", f"OUT={out}"], capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"make -C tests/emu failed:\n{r.stdout}\n{r.stderr}")
-    L = C.CDLL(os.path.join(EMU_DIR, "libwx_emu.so"))
+    L = C.CDLL(os.path.join(EMU_DIR, out))
     L.wxe_render.restype = C.c_int
     L.wxe_render.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_int, C.c_uint32,
                              C.c_void_p]

@@ -103,3 +103,27 @@ def test_warp_statistics_are_consistent():
     assert sum(stats[f"combo{i}"] for i in range(8)) == stats["warp_steps"]
     assert stats["generic_iters"] <= stats["n5_blocks"] + stats["n4_blocks"] + stats["leaf_blocks"]
     assert stats["warp_steps"] * 32 >= stats["lane_steps"]
+
+
+def test_full_size_config3_sphere_4k():
+    """BASELINE config 3 at its full size on the CPU: the 2048^3 sphere level set (404 480 leaves) at 3840x2160, the bench
+    workload -- every pixel and AOV of the device code equal to the oracle's."""
+    import bench
+    import oracle_ffi as O
+    import woxel_b200 as W
+    _, flat, _, _ = bench.build_scene("sphere2048")
+    assert (flat.n5, flat.n4, flat.n3) == (8, 1208, 404480)
+    w, h = 3840, 2160
+    eye, target = bench.camera_for("sphere2048", 0)
+    ws = W.ComputeState.build(W.Camera(eye=eye, target=target, aspect=w / h), w, W.RenderMode.Gray)
+    rgba, aov, stats = E.render(flat.desc, ws, w, h, aov=True, stats=True)
+    ref_rgba, ref_aov, st = bench.oracle_gpudata(flat).render(bench.oracle_state(ws), w, h)
+    assert np.array_equal(rgba[0], ref_rgba)
+    for k in ("state", "voxel", "leaf", "level", "iters", "mask"):
+        assert np.array_equal(aov[k][0], ref_aov[k]), k
+    for k in ("depth", "pos"):
+        assert np.array_equal(_bits_nan_canonical(aov[k][0]), _bits_nan_canonical(ref_aov[k])), k
+    # the figures DESIGN.md quotes for this workload
+    assert stats["rays"] == w * h and stats["truncated"] == 0
+    assert 31.0 < stats["lane_steps"] / stats["rays"] < 31.8
+    assert 0.45 < (ref_aov["state"] == 0).mean() < 0.52

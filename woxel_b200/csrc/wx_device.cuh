@@ -64,7 +64,14 @@ struct DevTree {
   // not fit: scan origins), else the N5 index, | kRootBeyond when the cell reaches outside the world (its origin has a
   // component outside [-4096, 0]), where the march must test the bounds.  Outside the grid: scan origins.
   int16_t root_grid[64];
+#ifdef WX_ROOT_PTRS
+  // A/B variant: the same cells as ready-made N5 table addresses of THIS replica: kRootPtrNone = no N5, kRootPtrScan = scan the
+  // origins (both have bit 1 set), else the address of e5[n5] with bit 0 set when the cell reaches outside the world (tables
+  // are 128-B aligned, so bits 0..6 of an address are free).
+  uint64_t root_ptr[64];
+#endif
 };
+constexpr uint64_t kRootPtrNone = 2ull, kRootPtrScan = 6ull;
 
 struct AovPtrs {
   uint8_t* state;
@@ -343,6 +350,24 @@ __device__ __forceinline__ bool out_of_bounds(float x, float y, float z) {
 // `beyond`: the bounds test of :100-103 can succeed at this position (it cannot inside an N5 whose
 // origin lies in [-4096, 0]^3).
 __device__ __forceinline__ bool enter_root(const DevTree& T, Cursor& c, uint32_t& dv, uint32_t x, uint32_t y, uint32_t z) {
+#ifdef WX_ROOT_PTRS
+  const uint32_t c0 = (kBias >> 12) - 2u;
+  const uint32_t cx = (x >> 12) - c0, cy = (y >> 12) - c0, cz = (z >> 12) - c0;
+  uint64_t v = kRootPtrScan;
+  if ((cx | cy | cz) < 4u) v = T.root_ptr[cx * 16u + cy * 4u + cz];
+  if ((uint32_t)v & 2u) {  // no N5 here, or the cell's N5 must be found by the scan
+    int n5 = -1;
+    if ((uint32_t)v & 4u) n5 = scan_roots(T, x, y, z);
+    if (n5 < 0) {
+      c.dbits = kNoCache;
+      return true;
+    }
+    v = (uint64_t)(T.e5 + (size_t)n5 * 32768u) | (reaches_beyond(x, y, z) ? 1ull : 0ull);
+  }
+  c.q5 = reinterpret_cast<const uint32_t*>(v & ~1ull);
+  dv = 128u;
+  return ((uint32_t)v & 1u) != 0u;
+#endif
   const int r = find_root(T, x, y, z);
   if (r < 0) {
     c.dbits = kNoCache;

@@ -157,6 +157,13 @@ static inline void fill_dev_tree(DevTree& T, const uint32_t* e5, const uint32_t*
   T.leaf_shift = leaf_shift;
   T.fast_ok = fast_ok ? 1u : 0u;
   memcpy(T.root_grid, root_grid, sizeof(T.root_grid));
+#ifdef WX_ROOT_PTRS
+  for (int c = 0; c < 64; ++c) {
+    const int v = root_grid[c];
+    T.root_ptr[c] = v == kRootNone ? kRootPtrNone : v == kRootScan ? kRootPtrScan
+                    : ((uint64_t)(e5 + (size_t)(v & kRootIndexMask) * 32768u) | ((v & kRootBeyond) ? 1ull : 0ull));
+  }
+#endif
 }
 
 }  // namespace wx
