@@ -65,7 +65,8 @@ struct DevTree {
   // component outside [-4096, 0]), where the march must test the bounds.  Outside the grid: scan origins.
   int16_t root_grid[64];
 #ifdef WX_ROOT_PTRS
-  // A/B variant: the same cells as ready-made N5 table addresses of THIS replica: kRootPtrNone = no N5, kRootPtrScan = scan the
+  // A/B variant (measured 0.7 % SLOWER than the int16 cells + address arithmetic, profiles/r1_variants_h.txt; not the default):
+  // the same cells as ready-made N5 table addresses of THIS replica: kRootPtrNone = no N5, kRootPtrScan = scan the
   // origins (both have bit 1 set), else the address of e5[n5] with bit 0 set when the cell reaches outside the world (tables
   // are 128-B aligned, so bits 0..6 of an address are free).
   uint64_t root_ptr[64];
@@ -367,7 +368,7 @@ __device__ __forceinline__ bool enter_root(const DevTree& T, Cursor& c, uint32_t
   c.q5 = reinterpret_cast<const uint32_t*>(v & ~1ull);
   dv = 128u;
   return ((uint32_t)v & 1u) != 0u;
-#endif
+#else
   const int r = find_root(T, x, y, z);
   if (r < 0) {
     c.dbits = kNoCache;
@@ -376,6 +377,7 @@ __device__ __forceinline__ bool enter_root(const DevTree& T, Cursor& c, uint32_t
   c.q5 = T.e5 + (size_t)(r & ~kRootBeyond) * 32768u;
   dv = 128u;
   return (r & kRootBeyond) != 0;
+#endif
 }
 
 // One lookup L(pos) through the cursor, for the exact march (bounds tested every step).
