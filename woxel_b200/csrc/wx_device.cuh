@@ -258,7 +258,19 @@ leaf:
 }
 #else
 // One structured `if` per level: the lanes of a warp reconverge before the leaf level, whatever mix of start
-// levels they have.
+// levels they have.  ptxas threads the jump from "the N5 entry is a child" straight into the N4 block, so lanes that
+// came down from the N5 and lanes that started at the N4 run that block one group after the other (ncu: 6.1 M
+// executions at 16 lanes where 4.8 M at 20 would do); WX_JOIN makes the level opaque at the join so that the groups
+// meet there first (-DWX_DESCEND_JOIN, A/B).
+#ifdef WX_DESCEND_JOIN
+#ifdef WX_HOST_EMU
+#define WX_JOIN(lvl) ((void)0)
+#else
+#define WX_JOIN(lvl) asm volatile("" : "+r"(lvl))
+#endif
+#else
+#define WX_JOIN(lvl) ((void)0)
+#endif
 template <bool WIDE>
 __device__ __forceinline__ float descend(const DevTree& T, Cursor& c, uint32_t dv, uint32_t x, uint32_t y, uint32_t z) {
   float size = 0.f;
@@ -271,6 +283,7 @@ __device__ __forceinline__ float descend(const DevTree& T, Cursor& c, uint32_t d
       c.q4 = reinterpret_cast<const uint32_t*>(T.e4_adj + (uint64_t)e * 16384ull), lvl = 4u;
     }
   }
+  WX_JOIN(lvl);
   if (lvl == 4u) {
     const uint32_t e = __ldg(c.q4 + (((x << 5) & 0xF00u) | ((y << 1) & 0xF0u) | ((z >> 3) & 15u)));
     if ((int32_t)e >= 0) {
@@ -451,7 +464,7 @@ static __device__ __noinline__ HitOut march_exact(const DevTree& T, V3 src, V3 d
 //      is at least 1/(2 size) away from every integer, and fma(x, r, r/2) with r = MUFU.RCP(size)
 //      is within 4097.5 * 2^-21.4 / size < 1/(2 size) of it (|x| <= 4096 when the bounds test has
 //      passed), so its floor is exact.  size * that floor is an integer below 2^24: the FMA that
-//      forms it from the round-down add is exact.  (The one input this changes is a denormal
+//      subtracts p from it rounds once, exactly like p - size * floor(p / size).  (The one input this changes is a denormal
 //      negative p, where RN(p/size) underflows to -0: not reachable from a camera.)
 //  (3) size * step01 is exactly size or 0, so fma(size, step01, -m) rounds once, like the WGSL.
 //  (4) mask: without NaNs, (tx <= ty && tx <= tz) == (tx == min(tx, ty, tz)).
@@ -508,15 +521,25 @@ struct FastRay {
     }
     const float r = rcp_approx(size);
     const float hr = 0.5f * r;
-    const float nms = -kMagic * size;
     const f32x2 xfxy = add2(txy, bc(-kMagic));                         // float(floor(p)), exact
     const float xfz = tz - kMagic;
     const f32x2 qxy = add2_rd(fma2(xfxy, bc(r), bc(hr)), bc(kMagic));  // kMagic + floor(p / size)
     const float qz = __fadd_rd(fmaf(xfz, r, hr), kMagic);
+#ifndef WX_NM_SEPARATE
+    // k = floor(p / size) = q - kMagic (exact), then -modulo_vec3f(p, size) = fma(k, size, -p): k * size is an exact integer
+    // below 2^24, so this rounds once, like g - p.  (One instruction fewer than forming g first: measured 0.7 % faster,
+    // profiles/r1_variants_h.txt.)
+    const f32x2 kxy = add2(qxy, bc(-kMagic));
+    const float kz = qz - kMagic;
+    const f32x2 nmxy = fma2(kxy, bc(size), pk(-lo(pxy), -hi(pxy)));
+    const float nmz = fmaf(kz, size, -pz);
+#else  // A/B: g = size * floor(p / size) first, then g - p
+    const float nms = -kMagic * size;
     const f32x2 gxy = fma2(qxy, bc(size), bc(nms));                    // size * floor(p / size), exact
     const float gz = fmaf(qz, size, nms);
     const f32x2 nmxy = sub2(gxy, pxy);                                 // -modulo_vec3f(p, size)
     const float nmz = gz - pz;
+#endif
     const f32x2 tmxy = mul2(ixy, fma2(bc(size), s01xy, nmxy));         // tMax
     const float tmz = iz * fmaf(size, s01z, nmz);
     ltx = lo(tmxy), lty = hi(tmxy), ltz = tmz;
