@@ -1,0 +1,68 @@
+"""Two independent restatements of raycast.comp.wgsl must agree bit for bit: oracle/wxo_render.c (C, per pixel, with the
+shader's parent cache, on flat tables) and oracle/wgsl_numpy.py (numpy float32, all rays at once, every lookup from the
+root, on the reference's own atlas textures + u32 mask words + origins).  A transcription error in either one -- or in the
+atlas / mask serialisation they do NOT share -- shows up here.  (Neither is pinned to an execution of the reference:
+"parity unpinned")"""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import scenes
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+import wgsl_numpy as WN  # noqa: E402
+
+
+def numpy_scene(s):
+    g = s.gpu
+    return WN.Scene(g.atlas(0), g.atlas(1), g.atlas(2), *(g.mask(i) for i in range(5)), g.origins)
+
+
+def compare(name, st, w, h):
+    s = scenes.get_scene(name)
+    rgba, hit = WN.cp_main(numpy_scene(s), bytes(st), w, h)
+    ref_rgba, ref, _ = s.gpu.render(st, w, h)
+    dw, dh = (w // 8) * 8, (h // 4) * 4
+    assert np.array_equal(hit["state"], ref["state"][:dh, :dw]), name
+    assert np.array_equal(hit["i"], ref["iters"][:dh, :dw]), name
+    assert np.array_equal(hit["num_parents"], ref["level"][:dh, :dw]), name
+    bits = lambda a: np.ascontiguousarray(a, np.float32).view(np.uint32)
+    nan = np.isnan(hit["p"])
+    assert np.array_equal(nan, np.isnan(ref["pos"][:dh, :dw]))
+    assert np.array_equal(bits(hit["p"])[~nan], bits(ref["pos"][:dh, :dw])[~nan]), name
+    m = hit["mask"]
+    assert np.array_equal(m[..., 0] | (m[..., 1].astype(np.uint8) << 1) | (m[..., 2].astype(np.uint8) << 2), ref["mask"][:dh, :dw]), name
+    leaf = np.where(hit["num_parents"] == 3, hit["leaf"].astype(np.int64), -1)
+    assert np.array_equal(leaf, ref["leaf"][:dh, :dw]), name
+    assert np.array_equal(np.floor(hit["p"]).astype(np.int64)[~nan], ref["voxel"][:dh, :dw].astype(np.int64)[~nan]), name
+    assert np.array_equal(rgba, ref_rgba), (name, int((rgba != ref_rgba).any(-1).sum()))
+
+
+@pytest.mark.parametrize("name", ["cube", "icosahedron"])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3, 4])
+def test_assets_all_modes(name, mode):
+    eye, target = scenes.CAMERAS["oblique_a" if mode in (1, 3) else ("oblique_b" if mode == 4 else "default")]
+    st = scenes.state_for(eye, target, 96, 64, mode=mode, show_grid=(1, 1, 1) if mode < 3 else (0, 0, 0))
+    compare(name, st, 96, 64)
+
+
+@pytest.mark.parametrize("name,eye,target", [
+    ("small_sphere", (90.5, 70.5, -120.5), (0.0, 0.0, 0.0)),
+    ("scattered", (10.5, 20.5, -900.5), (0.0, 0.0, 0.0)),
+    ("beyond_bounds", (4000.5, 30.5, -150.5), (4100.0, 3.0, 3.0)),
+    ("slab", (0.5, 4.0, -300.5), (0.5, 4.0, 0.5)),
+    ("long_slab", (-900.5, 4.0005, 0.5), (0.5, 4.0005, 0.5)),
+    ("active_tiles", (90.5, 70.5, -120.5), (0.0, 0.0, 0.0)),
+    ("empty_leaf", (90.5, 70.5, -120.5), (0.0, 0.0, 0.0)),
+])
+@pytest.mark.parametrize("mode", [0, 4])
+def test_edge_scenes(name, eye, target, mode):
+    st = scenes.state_for(eye, target, 64, 40, mode=mode)
+    compare(name, st, 64, 40)
+
+
+def test_ragged_frame_and_outside_eye():
+    compare("cube", scenes.state_for(*scenes.CAMERAS["default"], 45, 30, mode=3), 45, 30)
+    compare("small_sphere", scenes.state_for((0.5, 0.5, -5000.5), (0.5, 0.5, 0.5), 32, 16, mode=2), 32, 16)

@@ -1,6 +1,7 @@
 // wx_raycast.cu -- the raycast kernels (cp_main of the reference, src/shaders/raycast.comp.wgsl:60-68)
-// and their launcher.  One thread per primary ray; a warp is an 8x4 pixel tile (the reference's
-// workgroup shape, so that the rays of a warp walk the same nodes); a CTA is 2x2 such tiles.
+// and their launcher.  One thread per primary ray; a warp is a 4x8-pixel tile (the reference's workgroup
+// is 8x4; the taller shape measured faster, see WX_WARP_W), a CTA is four such tiles side by side (16x8
+// pixels).  The per-pixel code (render_pixel, shade_and_store) lives in wx_device.cuh.
 #include <algorithm>
 #include <cstdlib>
 #include <string>
@@ -30,7 +31,7 @@ constexpr int kThreads = 32 * WX_CTA_WARPS;
 #define WX_MIN_BLOCKS (36 / WX_CTA_WARPS)  // resident CTAs per SM the register budget is capped for (36 warps -> 56 registers)
 #endif
 
-// Tiled kernel: one thread per pixel of the grid, a warp per 8x4 tile, a CTA per 2x2 tiles.
+// Tiled kernel: one thread per pixel of the grid, a warp per 4x8-pixel tile, a CTA per four tiles (16x8 pixels).
 template <int MODE, bool AOV>
 __global__ void __launch_bounds__(kThreads, WX_MIN_BLOCKS) raycast_kernel(const __grid_constant__ RenderParams P) {
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
