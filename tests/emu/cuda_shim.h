@@ -62,6 +62,12 @@ static inline int __float2int_rn(float v) {  // cvt.rni.s32.f32: round half to e
 }
 template <class T>
 static inline T __ldg(const T* p) { return *p; }
+// atomics of the work queue (sequentially consistent here; the protocol relies on atomicity only)
+static inline uint32_t atomicAdd(uint32_t* p, uint32_t v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+static inline uint32_t atomicCAS(uint32_t* p, uint32_t compare, uint32_t val) {
+  __atomic_compare_exchange_n(p, &compare, val, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST);
+  return compare;  // the old value, as CUDA returns it
+}
 
 // rcp.approx.ftz.f32 stand-in
 extern thread_local int wx_emu_rcp_bump;  // ulps added to RN(1/v): -1, 0, +1

@@ -10,6 +10,7 @@
 
 #include <vector>
 
+#include "../../woxel_b200/csrc/wx_internal.h"
 #include "../../woxel_b200/csrc/wx_pack.h"
 
 thread_local int wx_emu_rcp_bump = 0;
@@ -137,4 +138,71 @@ extern "C" int wxe_render(const WxTreeDesc* d, const WxState* states, uint32_t n
   if (stats)
     for (int i = 0; i < WXE_N_STATS; ++i) stats[i] = acc[i].load();
   return WX_OK;
+}
+
+// The ticket protocol of raycast_persistent_cta with real threads: n_ctas "CTAs" of warps_per_cta "warps" (one thread each, the
+// role of lane 0) pull (chunk, tile) tickets until the queue says done.  counts[chunk * 16 + tile] receives how often each tile
+// was handed out (must be exactly 1 everywhere); returns the number of chunks rendered privately after a lost publish race.
+extern "C" int wxe_queue_sim(uint32_t n_chunks, uint32_t n_ctas, uint32_t warps_per_cta, uint32_t* counts, uint32_t seed) {
+  using namespace wx;
+  RenderParams P;
+  memset(&P, 0, sizeof(P));
+  uint32_t counter = 0;
+  P.work_counter = &counter;
+  P.n_chunks = n_chunks;
+  std::vector<uint32_t> state(n_ctas, 16u);  // as the kernel initialises s_state
+  std::atomic<int> privately{0}, bad{0};
+  std::vector<std::thread> th;
+  for (uint32_t c = 0; c < n_ctas; ++c)
+    for (uint32_t w = 0; w < warps_per_cta; ++w)
+      th.emplace_back([&, c, w]() {
+        uint32_t rng = seed * 2654435761u + c * 97u + w * 7919u + 1u;
+        uint32_t priv = kNoTile;
+        for (;;) {
+          const bool was_private = priv != kNoTile;
+          uint32_t t = 0;
+          const uint32_t chunk = next_ticket(P, &state[c], priv, t);
+          if (chunk == kNoTile) break;
+          if (!was_private && priv != kNoTile) privately.fetch_add(1);
+          if (chunk >= n_chunks || t >= 16u) {
+            bad.fetch_add(1);
+            break;
+          }
+          __atomic_fetch_add(&counts[(size_t)chunk * 16u + t], 1u, __ATOMIC_RELAXED);
+          rng = rng * 1664525u + 1013904223u;  // uneven "tile render times" to shake the interleavings
+          for (volatile uint32_t spin = 0; spin < ((rng >> 24) & 63u) * 8u; ++spin) {
+          }
+          if ((rng >> 20 & 15u) == 0u) std::this_thread::yield();
+        }
+      });
+  for (auto& t : th) t.join();
+  return bad.load() ? -1 : privately.load();
+}
+
+// Pixel coverage of the chunk / tile / lane mapping of raycast_persistent_cta for one shard of a frame, with the launch geometry
+// of launch_raycast (wx_raycast.cu): hits[y * width + x] += 1 for every in-frame pixel some (chunk, tile, lane) maps to.
+extern "C" int wxe_chunk_coverage(uint32_t width, uint32_t height, uint32_t shard_index, uint32_t shard_count, uint32_t band_rows,
+                                  uint32_t n_cams, uint32_t* hits) {
+  using namespace wx;
+  RenderParams P;
+  memset(&P, 0, sizeof(P));
+  P.width = width, P.height = height, P.row_base = 0, P.row_end = height;
+  P.disp_w = (width / 8) * 8, P.disp_h = (height / 4) * 4;
+  if (shard_count <= 1 || band_rows == 0) {
+    P.shard_index = 0, P.shard_count = 1, P.band_rows = ((height + 7) / 8) * 8, P.own_bands = 1;
+  } else {
+    P.shard_index = shard_index, P.shard_count = shard_count, P.band_rows = band_rows;
+    P.own_bands = shard_own_bands(height, shard_index, shard_count, band_rows);
+  }
+  const uint64_t own_rows = (uint64_t)P.own_bands * P.band_rows;
+  P.chunks_x = (width + 31u) / 32u;
+  P.chunks_y = (uint32_t)((own_rows + 15u) / 16u);
+  P.n_chunks = P.chunks_x * P.chunks_y * n_cams;
+  for (uint32_t chunk = 0; chunk < P.n_chunks; ++chunk)
+    for (uint32_t t = 0; t < 16; ++t)
+      for (uint32_t lane = 0; lane < 32; ++lane) {
+        const PixelRef q = pixel_of_chunk_tile(P, chunk, t, lane);
+        if (q.in_frame) hits[((size_t)q.cam * height + q.y) * width + q.x] += 1;
+      }
+  return 0;
 }

@@ -28,6 +28,10 @@ def lib() -> C.CDLL:
     L.wxe_render.restype = C.c_int
     L.wxe_render.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_int, C.c_uint32,
                              C.c_void_p]
+    L.wxe_queue_sim.restype = C.c_int
+    L.wxe_queue_sim.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32]
+    L.wxe_chunk_coverage.restype = C.c_int
+    L.wxe_chunk_coverage.argtypes = [C.c_uint32] * 6 + [C.c_void_p]
     L.wxe_n_stats.restype = C.c_int
     assert L.wxe_n_stats() == len(STAT_NAMES)
     return L
@@ -64,3 +68,19 @@ def render(desc, states, width: int, height: int, aov: bool = True, rcp_bump: in
     if rc != 0:
         raise RuntimeError(f"wxe_render failed: {rc}")
     return rgba, out, (dict(zip(STAT_NAMES, (int(v) for v in st))) if st is not None else None)
+
+
+def queue_sim(n_chunks: int, n_ctas: int, warps_per_cta: int = 4, seed: int = 1):
+    """The ticket protocol of the CTA-level work queue run by real threads.  Returns (counts[n_chunks, 16], private chunks)."""
+    counts = np.zeros((n_chunks, 16), np.uint32)
+    r = lib().wxe_queue_sim(n_chunks, n_ctas, warps_per_cta, counts.ctypes.data, seed)
+    if r < 0:
+        raise RuntimeError("wxe_queue_sim: a ticket outside the frame was handed out")
+    return counts, r
+
+
+def chunk_coverage(width: int, height: int, shard_index: int = 0, shard_count: int = 1, band_rows: int = 0, n_cams: int = 1):
+    """How often each pixel is reached by the (chunk, tile, lane) mapping of the CTA-level work queue for one shard."""
+    hits = np.zeros((n_cams, height, width), np.uint32)
+    lib().wxe_chunk_coverage(width, height, shard_index, shard_count, band_rows, n_cams, hits.ctypes.data)
+    return hits

@@ -63,3 +63,15 @@ def test_no_cpu_fallback():
             if f.endswith((".py", ".cpp", ".hpp", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "oracle_ffi" not in text and "libwxo" not in text and "wxo_" not in text, f
+                assert "emu_ffi" not in text and "libwx_emu" not in text and "wxe_" not in text, f
+
+
+def test_product_libraries_carry_no_emulation_code():
+    """tests/emu compiles wx_device.cuh for the host behind WX_HOST_EMU; the shipped libraries are built without it:
+    no emulation or oracle symbol is defined or referenced by them."""
+    import subprocess
+    for so in ("libwoxel_b200.so", "libwoxel_host.so"):
+        out = subprocess.run(["nm", "-D", "--defined-only", os.path.join(ROOT, "woxel_b200", so)], capture_output=True, text=True, check=True).stdout
+        und = subprocess.run(["nm", "-D", "--undefined-only", os.path.join(ROOT, "woxel_b200", so)], capture_output=True, text=True, check=True).stdout
+        for needle in ("wx_emu", "wxe_", "wxo_"):
+            assert needle not in out and needle not in und, (so, needle)

@@ -127,3 +127,31 @@ def test_full_size_config3_sphere_4k():
     assert stats["rays"] == w * h and stats["truncated"] == 0
     assert 31.0 < stats["lane_steps"] / stats["rays"] < 31.8
     assert 0.45 < (ref_aov["state"] == 0).mean() < 0.52
+
+
+@pytest.mark.parametrize("n_chunks,n_ctas,warps", [(0, 3, 4), (1, 4, 4), (5, 8, 4), (257, 6, 4), (2000, 8, 4), (300, 1, 1), (64, 16, 2)])
+def test_cta_queue_hands_out_every_tile_exactly_once(n_chunks, n_ctas, warps):
+    """The ticket protocol of raycast_persistent_cta (next_ticket, wx_device.cuh) under real concurrency: every tile of every
+    chunk is handed out exactly once, whatever the interleaving, including the lost-publish path (a warp keeps the chunk it
+    fetched for itself) and the end of the frame."""
+    for seed in range(1, 6):
+        counts, private = E.queue_sim(n_chunks, n_ctas, warps, seed)
+        assert (counts == 1).all(), (seed, int((counts != 1).sum()), private)
+
+
+@pytest.mark.parametrize("w,h,count,band,cams", [(64, 32, 1, 0, 1), (100, 50, 1, 0, 2), (13, 7, 1, 0, 1), (640, 360, 3, 8, 1), (328, 203, 4, 16, 2),
+                                                 (96, 44, 2, 8, 3)])
+def test_cta_queue_pixel_mapping_covers_every_owned_pixel_once(w, h, count, band, cams):
+    """chunk -> tile -> lane -> pixel of raycast_persistent_cta: every pixel of the rows a shard owns exactly once, nothing else."""
+    import ctypes as C
+    from woxel_b200 import _ffi
+    total = np.zeros((cams, h, w), np.uint32)
+    for idx in range(count):
+        hits = E.chunk_coverage(w, h, idx, count, band, cams)
+        if count > 1:  # the rows of this shard, from the product's own wx_shard_rows
+            rows = np.zeros(h, np.uint8)
+            sh = _ffi.WxShard(idx, count, band, 0)
+            assert _ffi.cuda_lib().wx_shard_rows(h, C.byref(sh), rows.ctypes.data) == 0
+            assert ((hits > 0).any(axis=(0, 2)) == (rows != 0)).all()
+        total += hits
+    assert (total == 1).all()

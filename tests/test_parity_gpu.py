@@ -422,6 +422,25 @@ def test_persistent_work_queue_kernel_is_bit_identical():
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
 
 
+def test_experimental_cta_queue_kernel_is_bit_identical():
+    """WX_KERNEL=persistent_cta: the persistent kernel with a CTA-level chunk queue (wx_raycast.cu).  It was written after the
+    round's GPU time was spent: its ticket protocol and pixel mapping are checked on the CPU (tests/test_device_emu.py), the
+    kernel itself has not run yet.  Opt-in until it has: WX_TEST_EXPERIMENTAL=1 python -m pytest tests -m gpu -k cta_queue"""
+    import os
+    import subprocess
+    import sys
+    if os.environ.get("WX_TEST_EXPERIMENTAL") != "1":
+        pytest.skip("experimental kernel, not yet run on a GPU: set WX_TEST_EXPERIMENTAL=1")
+    if os.environ.get("WX_KERNEL") == "persistent_cta":
+        pytest.skip("already running under the CTA-queue kernel")
+    env = dict(os.environ, WX_KERNEL="persistent_cta")
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(here, "test_parity_gpu.py"), "-m", "gpu", "-x", "-q", "-k",
+                        "assets_all_modes or edge_cases or camera_batch_and_shards or synthetic_scenes or zero_directions"],
+                       env=env, capture_output=True, text=True, timeout=1200)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+
+
 def test_randomized_scenes_and_cameras(gpu_ctx):
     """Differential fuzz (seeded): random sparse trees incl. far-apart and out-of-world N5s, random cameras (inside
     the volume, on integer coordinates, axis-aligned, outside the +-4096 world), every render mode -- bit-identical

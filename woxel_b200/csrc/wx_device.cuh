@@ -797,4 +797,53 @@ __device__ __forceinline__ void render_pixel(const RenderParams& P, const PixelR
   shade_and_store<MODE, AOV>(P, q, hdda_ray(P.tree, eye, dir), dir);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Work distribution of the persistent kernel with a CTA-level chunk queue (raycast_persistent_cta, wx_raycast.cu).  Lives here
+// so that tests/emu can run the ticket protocol with real threads on the CPU (tests/test_device_emu.py).
+// ---------------------------------------------------------------------------------------------
+constexpr uint32_t kQueueDone = 0xffffffffu, kNoTile = 0xffffffffu;
+
+__device__ __forceinline__ PixelRef pixel_of_chunk_tile(const RenderParams& P, uint32_t chunk, uint32_t t, uint32_t lane) {
+  const uint32_t per_cam = P.chunks_x * P.chunks_y;
+  const uint32_t cam_i = chunk / per_cam, rem = chunk - cam_i * per_cam;
+  const uint32_t cy = rem / P.chunks_x, cx = rem - cy * P.chunks_x;
+  PixelRef q;
+  q.x = cx * 32u + (t & 7u) * 4u + (lane & 3u);
+  const uint32_t vrow = cy * 16u + (t >> 3) * 8u + (lane >> 2);  // row among the rows this launch owns
+  const uint32_t band = (vrow / P.band_rows) * P.shard_count + P.shard_index;
+  q.y = P.row_base + band * P.band_rows + vrow % P.band_rows;
+  q.cam = P.cam_base + cam_i;
+  q.in_frame = q.x < P.width && q.y < P.row_end && vrow < P.own_bands * P.band_rows;
+  q.dispatched = q.x < P.disp_w && q.y < P.disp_h;
+  return q;
+}
+
+// Lane 0 of a warp: the next (chunk, tile) for this warp, or kNoTile when the frame is done.  `priv` is a chunk this warp
+// fetched but could not publish (another warp published one at the same moment): it renders that one by itself.
+__device__ __forceinline__ uint32_t next_ticket(const RenderParams& P, uint32_t* s_state, uint32_t& priv, uint32_t& tile_in_chunk) {
+  if (priv != kNoTile) {  // private chunk: tiles 1..15 (tile 0 was rendered when it was fetched)
+    const uint32_t chunk = priv >> 5, t = priv & 31u;
+    priv = t + 1u < 16u ? priv + 1u : kNoTile;
+    tile_in_chunk = t;
+    return chunk;
+  }
+  for (;;) {
+    const uint32_t old = atomicAdd(s_state, 0u);
+    if (old != kQueueDone && (old & 31u) < 16u) {
+      if (atomicCAS(s_state, old, old + 1u) != old) continue;
+      tile_in_chunk = old & 31u;
+      return old >> 5;
+    }
+    if (old == kQueueDone) return kNoTile;
+    const uint32_t g = atomicAdd(P.work_counter, 1u);
+    if (g >= P.n_chunks) {  // nothing left globally; a chunk published meanwhile by a CTA-mate is still served above
+      (void)atomicCAS(s_state, old, kQueueDone);
+      continue;
+    }
+    tile_in_chunk = 0u;
+    if (atomicCAS(s_state, old, (g << 5) | 1u) != old) priv = (g << 5) | 1u;  // lost the race: keep g for ourselves
+    return g;
+  }
+}
+
 }  // namespace wx

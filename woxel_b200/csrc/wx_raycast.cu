@@ -93,10 +93,45 @@ __global__ void __launch_bounds__(kThreads, WX_MIN_BLOCKS) raycast_persistent(co
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Persistent kernel with a CTA-level chunk queue (WX_KERNEL=persistent_cta; EXPERIMENTAL: written when the round's GPU
+// time was spent -- compiled, not yet run or measured; tests/test_parity_gpu.py holds an opt-in bit-identity test).
+// Why: in the tiled grid a CTA slot is held until its slowest warp ends (warp slots are 92.5 % used inside a CTA on the
+// bench frame, tools/warp_stats.py), and the warp-level queue above cures that but scatters the warps of a CTA over the
+// frame (their tiles no longer share nodes in L1).  Here the CTA owns a 32x16-pixel chunk; its warps take the chunk's 16
+// tiles (4x8 pixels, row-major: four consecutive tickets are a 16x8 strip, the tiled kernel's CTA footprint) from a
+// shared-memory ticket, and the first warp to find the chunk exhausted fetches the next chunk from the global counter
+// for everybody -- no barrier, nobody waits for the stragglers of the previous chunk.
+// s_state = chunk << 5 | tiles handed out (0..16); kQueueDone once the global counter ran out.
+// ---------------------------------------------------------------------------------------------
+template <int MODE, bool AOV>
+__global__ void __launch_bounds__(kThreads, WX_MIN_BLOCKS) raycast_persistent_cta(const __grid_constant__ RenderParams P) {
+  static_assert(kWarpW == 4, "the chunk layout below is written for 4x8-pixel warps");
+  __shared__ uint32_t s_state;
+  if (threadIdx.x == 0) s_state = 16u;  // "chunk 0 exhausted": the first warp to ask fetches a real one
+  __syncthreads();
+  const uint32_t lane = threadIdx.x & 31;
+  uint32_t priv = kNoTile;
+  for (;;) {
+    uint32_t chunk = kNoTile, t = 0;
+    if (lane == 0) chunk = next_ticket(P, &s_state, priv, t);
+    chunk = __shfl_sync(0xffffffffu, chunk, 0);
+    t = __shfl_sync(0xffffffffu, t, 0);
+    if (chunk == kNoTile) break;
+    render_pixel<MODE, AOV>(P, pixel_of_chunk_tile(P, chunk, t, lane));
+    __syncwarp();
+  }
+}
+
 template <int MODE>
-static cudaError_t launch_mode_persistent(const RenderParams& P, unsigned ctas, cudaStream_t stream) {
-  if (P.has_aov) raycast_persistent<MODE, true><<<ctas, kThreads, 0, stream>>>(P);
-  else raycast_persistent<MODE, false><<<ctas, kThreads, 0, stream>>>(P);
+static cudaError_t launch_mode_persistent(const RenderParams& P, unsigned ctas, cudaStream_t stream, bool cta_queue) {
+  if (cta_queue) {
+    if (P.has_aov) raycast_persistent_cta<MODE, true><<<ctas, kThreads, 0, stream>>>(P);
+    else raycast_persistent_cta<MODE, false><<<ctas, kThreads, 0, stream>>>(P);
+  } else {
+    if (P.has_aov) raycast_persistent<MODE, true><<<ctas, kThreads, 0, stream>>>(P);
+    else raycast_persistent<MODE, false><<<ctas, kThreads, 0, stream>>>(P);
+  }
   return cudaGetLastError();
 }
 
@@ -122,10 +157,12 @@ static cudaError_t launch_mode(const RenderParams& P, dim3 grid, cudaStream_t st
 // WX_KERNEL=persistent selects the work-queue kernel.  Measured on the 4K sphere frame (profiles/r1_variants_e.txt):
 // tiled 0.995 ms, persistent 1.006 ms -- the CTA tail the queue removes is not what limits the tiled grid, so the
 // simpler kernel is the default.
-static bool use_persistent() {
-  static const bool on = getenv("WX_KERNEL") && std::string(getenv("WX_KERNEL")) == "persistent";
-  return on;
+static int persistent_kind() {  // 0 tiled grid (default), 1 warp-level tile queue, 2 CTA-level chunk queue (experimental)
+  static const int kind = !getenv("WX_KERNEL") ? 0 : std::string(getenv("WX_KERNEL")) == "persistent" ? 1
+                          : std::string(getenv("WX_KERNEL")) == "persistent_cta" ? 2 : 0;
+  return kind;
 }
+static bool use_persistent() { return persistent_kind() != 0; }
 
 // Fills the launch geometry of P (shard -> bands -> tile rows) and launches frames
 // [P.cam_base, P.cam_base + n_cams) in render mode `render_mode` (the caller groups a camera batch
@@ -168,12 +205,13 @@ cudaError_t launch_raycast(RenderParams& P, uint32_t n_cams, uint32_t render_mod
       // one warp per tile at most; otherwise every resident CTA slot of the device
       const unsigned ctas = (unsigned)std::min<uint64_t>((n_chunks * 16 + WX_CTA_WARPS - 1) / WX_CTA_WARPS, resident_ctas ? resident_ctas : 148u * (unsigned)(WX_MIN_BLOCKS));
       *launches = 1;
+      const bool cta_queue = persistent_kind() == 2;
       switch (render_mode) {
-        case 1: return launch_mode_persistent<1>(P, ctas, stream);
-        case 2: return launch_mode_persistent<2>(P, ctas, stream);
-        case 3: return launch_mode_persistent<3>(P, ctas, stream);
-        case 4: return launch_mode_persistent<4>(P, ctas, stream);
-        default: return launch_mode_persistent<0>(P, ctas, stream);
+        case 1: return launch_mode_persistent<1>(P, ctas, stream, cta_queue);
+        case 2: return launch_mode_persistent<2>(P, ctas, stream, cta_queue);
+        case 3: return launch_mode_persistent<3>(P, ctas, stream, cta_queue);
+        case 4: return launch_mode_persistent<4>(P, ctas, stream, cta_queue);
+        default: return launch_mode_persistent<0>(P, ctas, stream, cta_queue);
       }
     }
   }
