@@ -66,3 +66,24 @@ def test_edge_scenes(name, eye, target, mode):
 def test_ragged_frame_and_outside_eye():
     compare("cube", scenes.state_for(*scenes.CAMERAS["default"], 45, 30, mode=3), 45, 30)
     compare("small_sphere", scenes.state_for((0.5, 0.5, -5000.5), (0.5, 0.5, 0.5), 32, 16, mode=2), 32, 16)
+
+
+@pytest.mark.parametrize("name", ["single_voxel", "offcentre_sphere", "small_sphere", "scattered"])
+def test_compute_sdf_two_restatements_agree(name):
+    """compute_sdf (vdb345.rs:290-628): the C oracle's sweep over flat arrays against oracle/sdf_python.py, a plain-Python
+    restatement on a pointer-style tree (written from the Rust text), value for value: N5 tiles, N4 tiles and every inactive
+    voxel.  One N5 (single_voxel, offcentre_sphere), eight N5s with the shell crossing all of them (small_sphere) and isolated
+    voxels in far-apart nodes (scattered) exercise the in-node, cross-node and background cases."""
+    import sdf_python as SP
+    s = scenes.get_scene(name)
+    k5, k4, v3 = scenes.bits2d(s.kids5), scenes.bits2d(s.kids4), scenes.bits2d(s.vals3)
+    root = SP.compute_sdf(SP.build(s.origins, k5, k4, v3))
+    t5, t4, t3 = SP.tables(root)
+    mine5 = np.array([[0 if v is None else v for v in row] for row in t5], np.uint64)
+    mine4 = np.array([[0 if v is None else v for v in row] for row in t4], np.uint64).reshape(-1, 4096)
+    mine3 = np.array([[0 if v is None else v for v in row] for row in t3], np.uint64).reshape(-1, 512)
+    assert mine5.shape == s.tab5.shape and mine4.shape == s.tab4.shape and mine3.shape == s.tab3.shape
+    assert np.array_equal(mine5[~k5], s.tab5[~k5].astype(np.uint64))
+    assert np.array_equal(mine4[~k4], s.tab4[~k4].astype(np.uint64))
+    assert np.array_equal(mine3[~v3], s.tab3[~v3].astype(np.uint64))
+    assert int(mine5[~k5].min()) >= 1 and int(mine3[~v3].min()) >= 1
