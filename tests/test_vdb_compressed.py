@@ -81,6 +81,44 @@ def test_blosc_multi_block_frames(tmp_path, blocksize):
         assert e.kind == "Leaf" and e.value == wbits
 
 
+@pytest.mark.parametrize("codec", ["blosclz", "zlib", "lz4"])
+@pytest.mark.parametrize("bit_shuffle", [False, True])
+@pytest.mark.parametrize("blocksize,half", [(None, True), (384, True), (1024, False), (4096, False)])
+def test_blosc_codecs_and_shuffles(tmp_path, codec, bit_shuffle, blocksize, half):
+    """The Blosc frame with each codec the reader decodes (BloscLZ = c-blosc's default codec, LZ4 = what OpenVDB writes, zlib)
+    and with byte or bit shuffle, single and multi-block, split and unsplit streams: the written voxels come back."""
+    pts, vals = sample_voxels(seed=5)
+    path = str(tmp_path / "c.vdb")
+    V.VdbWriter(compression=V.BLOSC | V.ACTIVE_MASK, half_float=half, blosc_blocksize=blocksize, blosc_codec=codec,
+                blosc_bit_shuffle=bit_shuffle).write(path, pts, vals)
+    v = W.VdbReader(path).read_vdb345_grid("ls_test")
+    assert v.count_leaf_values() == len(pts)
+    want = expected_bits(vals, half)
+    for p, wbits in zip(pts.tolist(), want.tolist()):
+        e = v.get_voxel(p)
+        assert e.kind == "Leaf" and e.value == wbits
+
+
+def test_blosclz_stream_forms():
+    """The stream forms a real BloscLZ encoder emits, fed to the product's decoder through one-leaf frames: long literal runs,
+    a long run (overlapping match at distance 1), length extensions of several bytes, and a far (16-bit) distance."""
+    import struct
+    rng = np.random.default_rng(3)
+    noise = rng.integers(0, 256, 9000, dtype=np.uint8).tobytes()
+    cases = [bytes(700), noise[:40] + bytes([7]) * 900 + noise[40:80], noise[:300] + noise[:300],
+             noise[:8500] + noise[100:500] + bytes(50), b"abc" * 400 + noise[:33], noise[:100] + bytes(70000) + noise[:100]]
+    for data in cases:
+        comp = V.blosclz_compress_block(data)
+        assert len(comp) < len(data)
+        # a one-stream Blosc frame around it (typesize 1, no shuffle, not split)
+        frame = struct.pack("<BBBBIII", 2, 1, 0x10 | (0 << 5), 1, len(data), len(data), 16 + 4 + 4 + len(comp)) + struct.pack("<i", 20) + \
+            struct.pack("<i", len(comp)) + comp
+        out = W.vdb.blosc_decompress(frame)
+        assert out == data
+    far = V.blosclz_compress_block(cases[3])
+    assert bytes([(7 << 5) | 31]) in far and len(far) < 8500 + 300  # the 400-byte repeat at distance 8400 went out as a far match
+
+
 def test_corrupt_blosc_frame_is_an_error_not_a_crash(tmp_path):
     pts, vals = sample_voxels()
     raw = bytearray(V.VdbWriter(compression=V.BLOSC | V.ACTIVE_MASK, half_float=True).build(pts, vals))
@@ -109,3 +147,33 @@ def test_compressed_model_renders(tmp_path):
         assert np.array_equal(getattr(fa, k), getattr(fb, k)), k
     inactive = ~scenes.bits2d(fa.vals3)
     assert np.array_equal(fa.tab3[inactive], fb.tab3[inactive])
+
+
+@pytest.mark.parametrize("codec", ["blosclz", "lz4", "zlib"])
+def test_mutated_blosc_frames_never_crash(codec):
+    """Bit flips, truncations and random words in Blosc frames of every codec: decoded bytes or a VdbError, never a crash or an
+    over-read (this test is part of the ASan + UBSan run, tools/asan_host.sh)."""
+    rng = np.random.default_rng(17)
+    base = (rng.integers(0, 4, 6000, dtype=np.uint8).astype(np.uint16) * 257).tobytes()
+    frames = [V.blosc_compress(base, 2, codec=codec), V.blosc_compress(base, 2, codec=codec, bit_shuffle=True, blocksize=1024),
+              V.blosc_compress(base, 4, codec=codec, blocksize=2048)]
+    ok = bad = 0
+    for f in frames:
+        assert W.vdb.blosc_decompress(f) == base
+        for _ in range(250):
+            m = bytearray(f)
+            kind = rng.integers(0, 3)
+            if kind == 0:
+                for _ in range(int(rng.integers(1, 4))):
+                    m[int(rng.integers(0, len(m)))] ^= 1 << int(rng.integers(0, 8))
+            elif kind == 1:
+                m = m[:int(rng.integers(0, len(m)))]
+            else:
+                at = int(rng.integers(0, max(1, len(m) - 4)))
+                m[at:at + 4] = rng.integers(0, 256, 4, dtype=np.uint8).tobytes()
+            try:
+                W.vdb.blosc_decompress(bytes(m))
+                ok += 1
+            except W.vdb.VdbError:
+                bad += 1
+    assert ok + bad == 750 and bad > 100

@@ -70,6 +70,73 @@ def lz4_compress_block(src: bytes) -> bytes:
     return bytes(out)
 
 
+def blosclz_compress_block(src: bytes) -> bytes:
+    """Greedy encoder of the BloscLZ / FastLZ level-2 stream format (3-byte hash matches): literal runs of 1..32 bytes
+    (control byte = count - 1), matches of 3.. bytes (control byte = min(len - 2, 7) << 5 | distance high bits, length
+    extension bytes, distance low byte; distances of 8192.. as the far form: 31 / 255 / 16-bit big-endian distance - 8192).
+    The stream starts with a literal run, as the format requires."""
+    n = len(src)
+    out = bytearray()
+    table: dict[bytes, int] = {}
+    lits = bytearray()
+
+    def flush_literals():
+        nonlocal lits
+        for k in range(0, len(lits), 32):
+            run = lits[k:k + 32]
+            out.append(len(run) - 1)
+            out.extend(run)
+        lits = bytearray()
+
+    i = 0
+    while i < n:
+        cand = table.get(src[i:i + 3]) if i + 3 <= n else None
+        if i + 3 <= n:
+            table[src[i:i + 3]] = i
+        dist = i - cand if cand is not None else 0
+        if cand is not None and i > 0 and dist <= 65535 + 8191 and (len(lits) > 0 or len(out) > 0):
+            m = 3
+            while i + m < n and src[cand + m] == src[i + m]:
+                m += 1
+            flush_literals()
+            v = m - 2
+            d = dist - 1
+            far = d >= 8191
+            hi = 31 if far else d >> 8
+            if v < 7:
+                out.append((v << 5) | hi)
+            else:
+                out.append((7 << 5) | hi)
+                r = v - 7
+                while r >= 255:
+                    out.append(255)
+                    r -= 255
+                out.append(r)
+            if far:
+                out.append(255)
+                out.extend(struct.pack(">H", d - 8191))
+            else:
+                out.append(d & 255)
+            i += m
+        else:
+            lits.append(src[i])
+            i += 1
+    flush_literals()
+    return bytes(out)
+
+
+def bitshuffle(data: bytes, typesize: int) -> bytes:
+    """c-blosc's bit shuffle of one block: the first (n // 8) * 8 elements become typesize * 8 bit rows (row j * 8 + b = bit b of
+    byte j of every element, element 8k + m in bit m of byte k of the row); the rest of the block is left as it is."""
+    a = np.frombuffer(data, np.uint8)
+    ne8 = (len(a) // typesize) // 8 * 8
+    head = a[:ne8 * typesize].reshape(ne8, typesize)
+    bits = np.unpackbits(head[:, :, None], axis=2, bitorder="little")          # [element, byte j, bit b]
+    rows = bits.transpose(1, 2, 0).reshape(typesize * 8, ne8)                  # row j * 8 + b, one bit per element
+    packed = np.packbits(rows, axis=1, bitorder="little")                      # element 8k + m -> bit m of byte k
+    return packed.tobytes() + a[ne8 * typesize:].tobytes()
+
+
 def shuffle(data: bytes, typesize: int) -> bytes:
     a = np.frombuffer(data, np.uint8)
     n = len(a) // typesize
@@ -77,7 +144,11 @@ def shuffle(data: bytes, typesize: int) -> bytes:
     return head.tobytes() + a[n * typesize:].tobytes()
 
 
-def blosc_compress(data: bytes, typesize: int, do_shuffle: bool = True, blocksize: int | None = None, force_memcpy: bool = False) -> bytes:
+BLOSC_CODECS = {"blosclz": 0, "lz4": 1, "zlib": 3}
+
+
+def blosc_compress(data: bytes, typesize: int, do_shuffle: bool = True, blocksize: int | None = None, force_memcpy: bool = False,
+                   codec: str = "lz4", bit_shuffle: bool = False) -> bytes:
     """A c-blosc 1.x frame with the LZ4 codec.  header: version 2, versionlz 1, flags (bit0 shuffle, bit1 memcpyed,
     bits 5-7 = 1: LZ4), typesize, nbytes, blocksize, cbytes; then int32 block offsets; a block is split into `typesize`
     streams when typesize <= 16 and blocksize / typesize >= 128 (never the leftover block); every stream is an int32
@@ -86,7 +157,9 @@ def blosc_compress(data: bytes, typesize: int, do_shuffle: bool = True, blocksiz
     if blocksize is None:
         blocksize = max(nbytes, 1)
     split = typesize <= 16 and blocksize // typesize >= 128
-    flags = (1 if do_shuffle and typesize > 1 else 0) | (0 if split else 0x10) | (1 << 5)
+    byte_sh = do_shuffle and typesize > 1 and not bit_shuffle
+    flags = (1 if byte_sh else 0) | (4 if bit_shuffle else 0) | (0 if split else 0x10) | (BLOSC_CODECS[codec] << 5)
+    encode = {"lz4": lz4_compress_block, "blosclz": blosclz_compress_block, "zlib": lambda b: zlib.compress(b, 6)}[codec]
     if force_memcpy or nbytes < 128:
         flags |= 2
         return struct.pack("<BBBBIII", 2, 1, flags, typesize, nbytes, blocksize, 16 + nbytes) + data
@@ -99,11 +172,13 @@ def blosc_compress(data: bytes, typesize: int, do_shuffle: bool = True, blocksiz
         leftover = len(chunk) < blocksize
         if flags & 1:
             chunk = shuffle(chunk, typesize)
+        elif flags & 4 and blocksize >= typesize:
+            chunk = bitshuffle(chunk, typesize)
         nsplits = typesize if (split and not leftover) else 1
         neblock = len(chunk) // nsplits
         for k in range(nsplits):
             part = chunk[k * neblock:(k + 1) * neblock] if nsplits > 1 else chunk
-            comp = lz4_compress_block(part)
+            comp = encode(part)
             if len(comp) >= len(part):
                 comp = part  # stored: a stream as long as its block is a plain copy
             body += struct.pack("<i", len(comp)) + comp
@@ -135,15 +210,17 @@ def _mask_bytes(bits: np.ndarray) -> bytes:
 
 
 class VdbWriter:
-    def __init__(self, compression: int = ACTIVE_MASK, half_float: bool = True, leaf_metadata: int = 0, blosc_blocksize: int | None = None):
+    def __init__(self, compression: int = ACTIVE_MASK, half_float: bool = True, leaf_metadata: int = 0, blosc_blocksize: int | None = None,
+                 blosc_codec: str = "lz4", blosc_bit_shuffle: bool = False):
         self.compression, self.half, self.md, self.blosc_blocksize = compression, half_float, leaf_metadata, blosc_blocksize
+        self.blosc_codec, self.blosc_bit_shuffle = blosc_codec, blosc_bit_shuffle
 
     # read.rs:490-574 mirrored
     def _blocks(self, raw: bytes, elem: int) -> bytes:
         if self.compression & BLOSC:
             if len(raw) == 0:
                 return struct.pack("<q", 0)
-            frame = blosc_compress(raw, elem, blocksize=self.blosc_blocksize)
+            frame = blosc_compress(raw, elem, blocksize=self.blosc_blocksize, codec=self.blosc_codec, bit_shuffle=self.blosc_bit_shuffle)
             if len(frame) >= len(raw) + 16 and not self.blosc_blocksize:
                 return struct.pack("<q", -len(raw)) + raw  # OpenVDB stores incompressible data raw with a negative size
             return struct.pack("<q", len(frame)) + frame

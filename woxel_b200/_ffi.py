@@ -119,6 +119,7 @@ HOST_API = {
     "wxh_vdb_count_nodes": (None, [vp, C.POINTER(C.c_uint64)]),
     "wxh_vdb_count_leaf_values": (C.c_uint64, [vp]),
     "wxh_vdb_compute_sdf": (None, [vp]),
+    "wxh_blosc_decompress": (C.c_int, [C.c_char_p, C.c_size_t, vp, C.c_size_t, C.POINTER(C.c_size_t)]),
     "wxh_vdb_read": (C.c_int, [C.c_char_p, C.c_char_p, C.POINTER(vp), C.POINTER(WxhVdbInfo)]),
     "wxh_vdb_to_flat": (vp, [vp, C.c_int]),
     "wxh_flat_free": (None, [vp]),

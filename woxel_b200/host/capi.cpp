@@ -115,6 +115,17 @@ extern "C" void wxh_vdb_count_nodes(const WxhVdb* v, uint64_t out[3]) {
 extern "C" uint64_t wxh_vdb_count_leaf_values(const WxhVdb* v) { return v->v.count_leaf_values(); }
 extern "C" void wxh_vdb_compute_sdf(WxhVdb* v) { v->v.compute_sdf(); }
 
+extern "C" int wxh_blosc_decompress(const uint8_t* frame, size_t n, uint8_t* out, size_t cap, size_t* out_len) {
+  if (!frame || !out_len || (!out && cap)) return WXH_ERR_INVALID_ARGUMENT;
+  return guarded([&]() {
+    const std::vector<uint8_t> v = vdb::decompress_blosc_frame(frame, n);
+    *out_len = v.size();
+    if (v.size() > cap) return (int)WXH_ERR_INVALID_ARGUMENT;  // *out_len says how much room is needed
+    if (!v.empty()) memcpy(out, v.data(), v.size());
+    return 0;
+  });
+}
+
 extern "C" int wxh_vdb_read(const char* path, const char* grid_name, WxhVdb** out, WxhVdbInfo* info) {
   if (!path || !grid_name || !out) return WXH_ERR_INVALID_ARGUMENT;
   *out = nullptr;

@@ -173,6 +173,9 @@ struct ArchiveHeader {
 // .vdb reader (read.rs).  Supports what the reference supports: file versions >= 218, no / zlib /
 // Blosc(LZ4, BloscLZ, zlib codecs; byte shuffle) block compression, active-mask compression,
 // half-float storage.
+// Decodes one c-blosc 1.x frame (BloscLZ / LZ4 / zlib codec, byte or bit shuffle); throws VdbError.
+std::vector<uint8_t> decompress_blosc_frame(const uint8_t* frame, size_t n);
+
 class VdbReader {
  public:
   explicit VdbReader(const std::string& path);

@@ -140,8 +140,9 @@ namespace {
 //           it is split: typesize <= 16, blocksize / typesize >= 128, not the shorter last block) or one,
 //           each an int32 byte count followed by the codec's output, or by the plain bytes when the count
 //           equals the stream size
-// OpenVDB writes these frames with blosc_compress_ctx(9, shuffle, sizeof(T), ..., "lz4"), so LZ4 (and zlib,
-// through the system library) are decoded; BloscLZ, Snappy, Zstd and bit shuffle report UnsupportedBloscFormat.
+// OpenVDB writes these frames with blosc_compress_ctx(9, shuffle, sizeof(T), ..., "lz4"); LZ4, BloscLZ (c-blosc's default
+// codec) and zlib (through the system library) are decoded, with byte or bit shuffle; Snappy and Zstd report
+// UnsupportedBloscFormat.
 // ---------------------------------------------------------------------------------------------
 bool lz4_decompress_block(const uint8_t* src, size_t n, uint8_t* dst, size_t cap) {
   size_t i = 0, o = 0;
@@ -180,6 +181,71 @@ bool lz4_decompress_block(const uint8_t* src, size_t n, uint8_t* dst, size_t cap
   return o == cap;
 }
 
+// BloscLZ (codec 0): c-blosc 1.x's own codec, the FastLZ level-2 stream format.  A control byte c (the first one is taken
+// modulo 32, i.e. the stream starts with literals): c < 32 -> c + 1 literal bytes follow; else a match of length
+// (c >> 5) - 1 + 3 (+ extension bytes, each added, while they are 255, when (c >> 5) == 7) at distance
+// ((c & 31) << 8) + next byte + 1; the pair (c & 31) == 31, next byte == 255 announces a 16-bit big-endian far distance to
+// which 8191 + 1 is added.  Matches may overlap their own output (runs).
+bool blosclz_decompress_block(const uint8_t* src, size_t n, uint8_t* dst, size_t cap) {
+  if (n == 0) return cap == 0;
+  size_t i = 0, o = 0;
+  uint32_t ctrl = src[i++] & 31u;
+  for (;;) {
+    if (ctrl >= 32u) {
+      size_t len = (ctrl >> 5) - 1u;
+      size_t dist = (size_t)(ctrl & 31u) << 8;
+      if (len == 6u) {
+        uint8_t x;
+        do {
+          if (i >= n) return false;
+          x = src[i++];
+          len += x;
+        } while (x == 255);
+      }
+      if (i >= n) return false;
+      const uint8_t code = src[i++];
+      dist += code;
+      if (code == 255 && (ctrl & 31u) == 31u) {
+        if (n - i < 2) return false;
+        dist = (((size_t)src[i] << 8) | src[i + 1]) + 8191u;
+        i += 2;
+      }
+      dist += 1;
+      len += 3;
+      if (dist > o || len > cap - o) return false;
+      for (size_t k = 0; k < len; ++k) dst[o + k] = dst[o + k - dist];
+      o += len;
+    } else {
+      const size_t run = (size_t)ctrl + 1u;
+      if (run > n - i || run > cap - o) return false;
+      memcpy(dst + o, src + i, run);
+      i += run, o += run;
+    }
+    if (i >= n) break;
+    ctrl = src[i++];
+  }
+  return o == cap;
+}
+
+// Undo c-blosc's bit shuffle of one block (flag bit 2): the first ne8 = (bsize / typesize) rounded down to a multiple of 8
+// elements are stored as typesize * 8 bit rows of ne8 / 8 bytes -- row (j * 8 + b) collects bit b (0 = least significant) of
+// byte j of every element, element 8k + m in bit m of the row's byte k; the remaining bytes of the block are stored as they are.
+void bit_unshuffle_block(const uint8_t* in, uint8_t* out, size_t bsize, size_t typesize) {
+  const size_t ne8 = (bsize / typesize) & ~(size_t)7, row = ne8 / 8;
+  memset(out, 0, ne8 * typesize);
+  for (size_t j = 0; j < typesize; ++j)
+    for (size_t b = 0; b < 8; ++b) {
+      const uint8_t* r = in + (j * 8 + b) * row;
+      for (size_t k = 0; k < row; ++k) {
+        const uint8_t v = r[k];
+        if (!v) continue;
+        for (size_t m = 0; m < 8; ++m)
+          if ((v >> m) & 1u) out[(8 * k + m) * typesize + j] |= (uint8_t)(1u << b);
+      }
+    }
+  memcpy(out + ne8 * typesize, in + ne8 * typesize, bsize - ne8 * typesize);
+}
+
 std::vector<uint8_t> blosc_decompress(const uint8_t* f, size_t n) {
   auto bad = [](const char* what) { return VdbError(VdbError::InvalidBloscData, std::string("Blosc frame: ") + what); };
   auto le32 = [&](size_t at) { return (uint32_t)f[at] | ((uint32_t)f[at + 1] << 8) | ((uint32_t)f[at + 2] << 16) | ((uint32_t)f[at + 3] << 24); };
@@ -194,10 +260,10 @@ std::vector<uint8_t> blosc_decompress(const uint8_t* f, size_t n) {
     memcpy(out.data(), f + 16, nbytes);
     return out;
   }
-  if (flags & 0x4) throw VdbError(VdbError::UnsupportedBloscFormat, "Blosc bit shuffle is not supported");
   const int codec = flags >> 5;
-  if (codec != 1 && codec != 3)
-    throw VdbError(VdbError::UnsupportedBloscFormat, "Blosc codec " + std::to_string(codec) + " is not supported (LZ4 and zlib are)");
+  if (codec != 0 && codec != 1 && codec != 3)
+    throw VdbError(VdbError::UnsupportedBloscFormat, "Blosc codec " + std::to_string(codec) + " is not supported (BloscLZ, LZ4 and zlib are)");
+  const bool byte_shuffled = (flags & 0x1) && typesize > 1, bit_shuffled = !byte_shuffled && (flags & 0x4) && blocksize >= typesize;
   if (blocksize == 0) throw bad("zero block size");
   const size_t nblocks = (nbytes + blocksize - 1) / blocksize;
   if (n < 16 + 4 * nblocks) throw bad("block offsets are cut off");
@@ -209,7 +275,7 @@ std::vector<uint8_t> blosc_decompress(const uint8_t* f, size_t n) {
     const size_t nsplits = (may_split && !leftover) ? typesize : 1;
     const size_t neblock = bsize / nsplits;
     size_t at = le32(16 + 4 * b);
-    uint8_t* dst = (flags & 0x1) && typesize > 1 ? tmp.data() : out.data() + b * blocksize;
+    uint8_t* dst = (byte_shuffled || bit_shuffled) ? tmp.data() : out.data() + b * blocksize;
     for (size_t k = 0; k < nsplits; ++k) {
       if (at + 4 > n) throw bad("stream header is cut off");
       const size_t cb = le32(at);
@@ -220,13 +286,17 @@ std::vector<uint8_t> blosc_decompress(const uint8_t* f, size_t n) {
         memcpy(d, f + at, neblock);
       } else if (codec == 1) {
         if (!lz4_decompress_block(f + at, cb, d, neblock)) throw bad("corrupt LZ4 stream");
+      } else if (codec == 0) {
+        if (!blosclz_decompress_block(f + at, cb, d, neblock)) throw bad("corrupt BloscLZ stream");
       } else {
         uLongf dlen = (uLongf)neblock;
         if (uncompress(d, &dlen, f + at, (uLong)cb) != Z_OK || dlen != neblock) throw bad("corrupt zlib stream");
       }
       at += cb;
     }
-    if ((flags & 0x1) && typesize > 1) {  // undo the byte shuffle of this block
+    if (bit_shuffled) {
+      bit_unshuffle_block(tmp.data(), out.data() + b * blocksize, bsize, typesize);
+    } else if (byte_shuffled) {  // undo the byte shuffle of this block
       const size_t ne = bsize / typesize;
       uint8_t* o = out.data() + b * blocksize;
       for (size_t j = 0; j < typesize; ++j)
@@ -426,5 +496,8 @@ VDB345 VdbReader::read_vdb345_grid(const std::string& name) {  // read.rs:123-14
   }
   return vdb;
 }
+
+// One Blosc frame, outside a file (tests; tools that meet Blosc buffers elsewhere).
+std::vector<uint8_t> decompress_blosc_frame(const uint8_t* frame, size_t n) { return blosc_decompress(frame, n); }
 
 }  // namespace woxel::vdb

@@ -203,6 +203,19 @@ class VDB345:
         return v
 
 
+def blosc_decompress(frame: bytes) -> bytes:
+    """One c-blosc 1.x frame as the reader meets them inside a .vdb (read.rs:514-533): BloscLZ / LZ4 / zlib, byte or bit shuffle."""
+    need = C.c_size_t(0)
+    if len(frame) >= 16:
+        need.value = int.from_bytes(frame[4:8], "little")
+    buf = C.create_string_buffer(max(need.value, 1))
+    n = C.c_size_t(0)
+    rc = _ffi.host_lib().wxh_blosc_decompress(frame, len(frame), buf, need.value, C.byref(n))
+    if rc != 0:
+        raise VdbError(rc, _ffi.host_lib().wxh_last_error().decode())
+    return buf.raw[:n.value]
+
+
 class VdbReader:
     """VdbReader (read.rs:55-141).  `read_vdb345_grid(name)` returns a VDB345."""
 
