@@ -87,3 +87,35 @@ def test_compute_sdf_two_restatements_agree(name):
     assert np.array_equal(mine4[~k4], s.tab4[~k4].astype(np.uint64))
     assert np.array_equal(mine3[~v3], s.tab3[~v3].astype(np.uint64))
     assert int(mine5[~k5].min()) >= 1 and int(mine3[~v3].min()) >= 1
+
+
+def test_randomized_scenes_and_cameras_two_restatements_agree():
+    """The same seeded fuzz the device code is held to (tests/test_device_emu.py, tests/test_parity_gpu.py), between the two
+    restatements of the shader: random sparse trees incl. out-of-world N5s and solid blocks, random cameras (inside the volume,
+    on lattice planes, axis-aligned, near the bounds), random render modes."""
+    import oracle_ffi as O
+    rng = np.random.default_rng(424242)
+    for case in range(5):
+        t = O.Tree()
+        for _ in range(int(rng.integers(1, 5))):
+            centre = rng.integers(-900, 900, 3) if rng.random() < 0.8 else rng.integers(-6000, 6000, 3)
+            ext = int(rng.integers(1, 40))
+            t.set_voxels((centre + rng.integers(-ext, ext + 1, size=(int(rng.integers(1, 300)), 3))).astype(np.int32))
+        if case % 2 == 0:
+            c0 = rng.integers(-100, 100, 3)
+            ax = [np.arange(c, c + int(rng.integers(2, 20))) for c in c0]
+            t.set_voxels(np.stack(np.meshgrid(*ax, indexing="ij"), -1).reshape(-1, 3).astype(np.int32))
+        s = scenes.OracleScene(t)
+        sc = numpy_scene(s)
+        for kind in range(6):
+            eye = [tuple(rng.uniform(-1500, 1500, 3)), tuple(float(v) for v in rng.integers(-300, 300, 3)),
+                   (float(rng.integers(-50, 50)) + 0.5, float(rng.integers(-50, 50)) + 0.5, -700.5), tuple(rng.uniform(-4090, 4090, 3)),
+                   tuple(rng.uniform(4000, 4300, 3)), tuple(rng.uniform(-60, 60, 3))][kind]
+            target = (eye[0], eye[1], eye[2] + 100.0) if kind == 2 else tuple(rng.uniform(-200, 200, 3))
+            st = scenes.state_for(eye, target, 48, 24, mode=int(rng.integers(0, 5)), show_grid=(1, 1, 1))
+            rgba, hit = WN.cp_main(sc, bytes(st), 48, 24)
+            ref_rgba, ref, _ = s.gpu.render(st, 48, 24)
+            assert np.array_equal(hit["state"], ref["state"]) and np.array_equal(hit["i"], ref["iters"]), (case, kind, eye, target)
+            nan = np.isnan(hit["p"])
+            assert np.array_equal(hit["p"].view(np.uint32)[~nan], ref["pos"].view(np.uint32)[~nan]), (case, kind)
+            assert np.array_equal(rgba, ref_rgba), (case, kind, eye, target)
