@@ -169,6 +169,21 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def measured_bytes_per_ray(prof: dict, rays_per_launch: int, hbm_peak_gbs: float):
+    """Bytes per ray the kernel moves at each level of the memory hierarchy (one ncu capture of the committed kernel,
+    profiles/traffic.json) and the rays/s each level's MEASURED peak bandwidth would allow at that traffic."""
+    try:
+        if not prof or not prof.get("l2_bytes_per_launch") or not rays_per_launch:
+            return None
+        l1, l2, dram = (prof.get(k, 0) / rays_per_launch for k in ("l1_bytes_per_launch", "l2_bytes_per_launch", "dram_bytes_per_launch"))
+        l2_peak = prof.get("l2_peak_gbs")
+        return {"l1": round(l1, 1), "l2": round(l2, 1), "dram": round(dram, 2), "l2_peak_gbs": l2_peak,
+                "rays_per_s_roofline_Grays": {"l2": round(l2_peak / l2, 1) if l2_peak and l2 else None,
+                                              "dram": round(hbm_peak_gbs / dram, 1) if hbm_peak_gbs and dram else None}}
+    except Exception:  # a reporting extra must never cost the bench line
+        return None
+
+
 # ------------------------------------------------------------------------------------------------
 # reference arm: the oracle port on the host cores
 # ------------------------------------------------------------------------------------------------
@@ -411,6 +426,8 @@ def main():
         if os.path.exists(tpath):
             prof = json.load(open(tpath)).get(args.scene, {})
             traffic, warp_instr = prof.get("dram_bytes_per_launch"), prof.get("warp_instructions_per_launch")
+        else:
+            prof = {}
         roof = None
         if bytes_per_ray is not None:
             achieved = bytes_per_ray * rays_per_frame / (ms_per_step * 1e-3) / 1e9  # per GPU: one launch = one frame
@@ -425,6 +442,9 @@ def main():
                         "warp_instructions_per_launch": warp_instr,
                         "frac_of_peak": round(warp_instr / (torch.cuda.get_device_properties(0).multi_processor_count * 4 *
                                                              clocks["sm_mhz"] * 1e6 * ms_per_step * 1e-3), 4)},
+                    # measured bytes per ray at each level of the hierarchy (one ncu capture, profiles/traffic.json) and the rays/s
+                    # each level's measured peak would allow: none of them is what limits the kernel
+                    "measured_bytes_per_ray": measured_bytes_per_ray(prof, rays_per_frame, peak),
                     "note": "algorithmic bytes (SURVEY 8d) over the CUDA-event time of the kernel, L2 flushed before each launch; "
                             "the working set is L2-resident so this is a bandwidth-equivalent figure, the kernel is latency/issue bound"}
         out = {

@@ -30,3 +30,16 @@ def test_other_ranks_of_the_reference_arm_exit_quietly():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"], capture_output=True, text=True,
                        timeout=120, cwd=ROOT, env=env)
     assert r.returncode == 0 and not [l for l in r.stdout.splitlines() if l.startswith("{")]
+
+
+def test_measured_bytes_per_ray_helper():
+    """The reporting extra of the roofline object: computed from profiles/traffic.json, None (never an exception) on odd input."""
+    import json
+    import os
+    import bench
+    prof = json.load(open(os.path.join(bench.ROOT, "profiles", "traffic.json")))["sphere2048"]
+    m = bench.measured_bytes_per_ray(prof, 3840 * 2160, 6541.8)
+    assert m["l1"] > m["l2"] > m["dram"] > 0 and m["rays_per_s_roofline_Grays"]["l2"] > 100 and m["rays_per_s_roofline_Grays"]["dram"] > 100
+    for bad in (None, {}, {"l2_bytes_per_launch": "x"}, {"l2_bytes_per_launch": 5}):
+        assert bench.measured_bytes_per_ray(bad, 10, 6541.8) is None or isinstance(bench.measured_bytes_per_ray(bad, 10, 6541.8), dict)
+    assert bench.measured_bytes_per_ray(prof, 0, 6541.8) is None
