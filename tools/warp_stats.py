@@ -36,8 +36,16 @@ def main():
     st = W.ComputeState.build(W.Camera(eye=eye, target=target, aspect=a.width / a.height), a.width, W.RenderMode(a.mode))
     for ww in a.warp_w:
         t1 = time.time()
-        _, _, s = E.render(flat.desc, st, a.width, a.height, aov=False, warp_w=ww, stats=True)
+        _, aov, s = E.render(flat.desc, st, a.width, a.height, aov=True, warp_w=ww, stats=True)
         ws = s["warp_steps"]
+        # warp slots a CTA of four warps side by side keeps busy: a slot is held until the CTA's slowest warp ends
+        import numpy as np
+        wh = 32 // ww
+        it = aov["iters"][0].astype(np.int64) + (aov["state"][0] != 2)  # lookups per primary ray
+        hh, wd = (a.height // wh) * wh, (a.width // (4 * ww)) * (4 * ww)
+        per_warp = it[:hh, :wd].reshape(hh // wh, wh, wd // ww, ww).max(axis=(1, 3))
+        per_cta = per_warp.reshape(per_warp.shape[0], -1, 4)
+        cta_slot_use = float(per_cta.sum() / (4 * per_cta.max(-1).sum()))
         out = {
             "scene": what, "frame": [a.width, a.height], "mode": a.mode, "warp_footprint": [ww, 32 // ww],
             "rays": s["rays"], "warps": s["warps"], "lane_steps": s["lane_steps"], "warp_steps": ws,
@@ -47,6 +55,7 @@ def main():
             "level_sets_touched": {"".join(n for b, n in ((1, "N5 "), (2, "N4 "), (4, "leaf ")) if i & b).strip() or "none":
                                    round(s[f"combo{i}"] / ws, 4) for i in range(8)},
             "table_reads_per_lane_step": round(s["lane_table_reads"] / s["lane_steps"], 3),
+            "warp_slot_use_inside_4_warp_cta": round(cta_slot_use, 4),
             "emu_s": round(time.time() - t1, 1), "scene_s": round(t1 - t0, 1),
         }
         print(json.dumps(out))
