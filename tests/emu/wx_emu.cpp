@@ -46,40 +46,53 @@ extern "C" int wxe_n_stats(void) { return WXE_N_STATS; }
 // Renders states[0..n_states) (each in its own render mode) exactly as wx_render would.  warp_w x (32 / warp_w) is the
 // pixel footprint of a warp for the lockstep statistics (stats may be null; they cover the primary rays of mode-0 style
 // marches only: secondary rays are traced into the same per-lane buffer after the primary one and are ignored).
+namespace {
+// The tables wx_tree_upload would send to the GPU, and the launch parameters of a whole-frame, single-shard launch.
+struct EmuScene {
+  std::vector<uint32_t> e5, e4;
+  std::vector<uint8_t> l3;
+  std::vector<int4> origins;
+  wx::RenderParams P;
+  int init(const WxTreeDesc* d, const WxState* states, uint32_t n_states, uint32_t width, uint32_t height, uint8_t* rgba, const WxAov* aov) {
+    using namespace wx;
+    uint32_t max5 = 0, max4 = 0, max3v = 0;
+    int rc = pack_internal(d->n5, 32768, 128.f, d->kids5, d->vals5, d->tab5, d->n4, e5, &max5);
+    if (rc) return rc;
+    rc = pack_internal(d->n4, 4096, 8.f, d->kids4, d->vals4, d->tab4, d->n3, e4, &max4);
+    if (rc) return rc;
+    const uint32_t leaf_bits = pack_leaves(d->n3, d->vals3, d->tab3, d->tab3_elem_bytes, l3, &max3v);
+    bias_origins(d->n5, d->origins, origins);
+    int16_t root_grid[64];
+    build_root_grid(d->n5, d->origins, root_grid);
+    // slack so that zero-sized levels have a base address
+    e5.push_back(0), e4.push_back(0), l3.push_back(0), origins.push_back(make_int4(0, 0, 0, 0));
+    memset(&P, 0, sizeof(P));
+    fill_dev_tree(P.tree, e5.data(), e4.data(), l3.data(), origins.data(), d->n5, d->n4, d->n3, leaf_bits == 8 ? 9 : 11,
+                  fast_march_ok(leaf_bits, max5, max4, max3v), root_grid);
+    P.n_states = n_states;
+    P.states = states;
+    P.s0 = states[0];
+    P.width = width, P.height = height;
+    P.disp_w = (width / 8) * 8, P.disp_h = (height / 4) * 4;  // wgpu_context.rs:281
+    P.row_end = height;
+    P.rgba = reinterpret_cast<uchar4*>(rgba);
+    if (aov) {
+      P.aov.state = aov->state, P.aov.voxel = aov->voxel, P.aov.leaf = aov->leaf, P.aov.level = aov->level;
+      P.aov.iters = aov->iters, P.aov.depth = aov->depth, P.aov.mask = aov->mask, P.aov.pos = aov->pos;
+      P.has_aov = 1u;
+    }
+    return 0;
+  }
+};
+}  // namespace
+
 extern "C" int wxe_render(const WxTreeDesc* d, const WxState* states, uint32_t n_states, uint32_t width, uint32_t height, uint8_t* rgba,
                           const WxAov* aov, int rcp_bump, uint32_t warp_w, uint64_t* stats) {
   if (!d || !states || !rgba || n_states == 0) return WX_ERR_INVALID_ARGUMENT;
-  std::vector<uint32_t> e5, e4;
-  std::vector<uint8_t> l3;
-  uint32_t max5 = 0, max4 = 0, max3v = 0;
-  int rc = pack_internal(d->n5, 32768, 128.f, d->kids5, d->vals5, d->tab5, d->n4, e5, &max5);
+  EmuScene scene;
+  const int rc = scene.init(d, states, n_states, width, height, rgba, aov);
   if (rc) return rc;
-  rc = pack_internal(d->n4, 4096, 8.f, d->kids4, d->vals4, d->tab4, d->n3, e4, &max4);
-  if (rc) return rc;
-  const uint32_t leaf_bits = pack_leaves(d->n3, d->vals3, d->tab3, d->tab3_elem_bytes, l3, &max3v);
-  std::vector<int4> origins;
-  bias_origins(d->n5, d->origins, origins);
-  int16_t root_grid[64];
-  build_root_grid(d->n5, d->origins, root_grid);
-  // slack so that zero-sized levels have a base address
-  e5.push_back(0), e4.push_back(0), l3.push_back(0), origins.push_back(make_int4(0, 0, 0, 0));
-
-  RenderParams P;
-  memset(&P, 0, sizeof(P));
-  fill_dev_tree(P.tree, e5.data(), e4.data(), l3.data(), origins.data(), d->n5, d->n4, d->n3, leaf_bits == 8 ? 9 : 11,
-                fast_march_ok(leaf_bits, max5, max4, max3v), root_grid);
-  P.n_states = n_states;
-  P.states = states;
-  P.s0 = states[0];
-  P.width = width, P.height = height;
-  P.disp_w = (width / 8) * 8, P.disp_h = (height / 4) * 4;  // wgpu_context.rs:281
-  P.row_end = height;
-  P.rgba = reinterpret_cast<uchar4*>(rgba);
-  if (aov) {
-    P.aov.state = aov->state, P.aov.voxel = aov->voxel, P.aov.leaf = aov->leaf, P.aov.level = aov->level;
-    P.aov.iters = aov->iters, P.aov.depth = aov->depth, P.aov.mask = aov->mask, P.aov.pos = aov->pos;
-    P.has_aov = 1u;
-  }
+  const RenderParams& P = scene.P;
   if (warp_w == 0 || 32 % warp_w) warp_w = 4;
   const uint32_t warp_h = 32 / warp_w;
   const uint32_t tiles_x = (width + warp_w - 1) / warp_w, tiles_y = (height + warp_h - 1) / warp_h;
@@ -205,4 +218,42 @@ extern "C" int wxe_chunk_coverage(uint32_t width, uint32_t height, uint32_t shar
         if (q.in_frame) hits[((size_t)q.cam * height + q.y) * width + q.x] += 1;
       }
   return 0;
+}
+
+// A whole frame through the work distribution of raycast_persistent_cta: n_ctas x warps_per_cta threads play the warps (each
+// renders the 32 lanes of its tile one after the other), pulling (chunk, tile) tickets exactly as the kernel's loop does; camera
+// batches render the states whose mode equals that of state 0 only if all modes are equal (one launch = one mode, as in wx_api).
+extern "C" int wxe_render_cta_queue(const WxTreeDesc* d, const WxState* states, uint32_t n_states, uint32_t width, uint32_t height,
+                                    uint8_t* rgba, const WxAov* aov, uint32_t n_ctas, uint32_t warps_per_cta) {
+  using namespace wx;
+  if (!d || !states || !rgba || n_states == 0 || n_ctas == 0 || warps_per_cta == 0) return WX_ERR_INVALID_ARGUMENT;
+  for (uint32_t i = 1; i < n_states; ++i)
+    if (states[i].render_mode[0] != states[0].render_mode[0]) return WX_ERR_INVALID_ARGUMENT;
+  EmuScene scene;
+  const int rc = scene.init(d, states, n_states, width, height, rgba, aov);
+  if (rc) return rc;
+  RenderParams& P = scene.P;
+  // launch geometry of launch_raycast for a single shard (wx_raycast.cu)
+  P.shard_index = 0, P.shard_count = 1, P.band_rows = ((height + 7) / 8) * 8, P.own_bands = 1;
+  P.chunks_x = (width + 31u) / 32u;
+  P.chunks_y = (P.band_rows + 15u) / 16u;
+  P.n_chunks = P.chunks_x * P.chunks_y * n_states;
+  uint32_t counter = 0;
+  P.work_counter = &counter;
+  const uint32_t mode = states[0].render_mode[0];
+  std::vector<uint32_t> state(n_ctas, 16u);
+  std::vector<std::thread> th;
+  for (uint32_t c = 0; c < n_ctas; ++c)
+    for (uint32_t w = 0; w < warps_per_cta; ++w)
+      th.emplace_back([&, c]() {
+        uint32_t priv = kNoTile;
+        for (;;) {
+          uint32_t t = 0;
+          const uint32_t chunk = next_ticket(P, &state[c], priv, t);
+          if (chunk == kNoTile) break;
+          for (uint32_t lane = 0; lane < 32; ++lane) pixel_mode(mode, P, pixel_of_chunk_tile(P, chunk, t, lane));
+        }
+      });
+  for (auto& t : th) t.join();
+  return WX_OK;
 }

@@ -30,6 +30,8 @@ def lib() -> C.CDLL:
                              C.c_void_p]
     L.wxe_queue_sim.restype = C.c_int
     L.wxe_queue_sim.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32]
+    L.wxe_render_cta_queue.restype = C.c_int
+    L.wxe_render_cta_queue.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]
     L.wxe_chunk_coverage.restype = C.c_int
     L.wxe_chunk_coverage.argtypes = [C.c_uint32] * 6 + [C.c_void_p]
     L.wxe_n_stats.restype = C.c_int
@@ -84,3 +86,26 @@ def chunk_coverage(width: int, height: int, shard_index: int = 0, shard_count: i
     hits = np.zeros((n_cams, height, width), np.uint32)
     lib().wxe_chunk_coverage(width, height, shard_index, shard_count, band_rows, n_cams, hits.ctypes.data)
     return hits
+
+
+def render_cta_queue(desc, states, width: int, height: int, n_ctas: int = 6, warps_per_cta: int = 4):
+    """A frame (or a batch of frames in one mode) through the work distribution of raycast_persistent_cta, played by CPU threads.
+    Returns (rgba[n,H,W,4], aov dict)."""
+    if not isinstance(states, (list, tuple)):
+        states = [states]
+    n = len(states)
+    buf = (C.c_char * (256 * n))()
+    for i, s in enumerate(states):
+        buf[256 * i:256 * (i + 1)] = bytes(s)
+    rgba = np.zeros((n, height, width, 4), np.uint8)
+    out = {
+        "state": np.zeros((n, height, width), np.uint8), "voxel": np.zeros((n, height, width, 3), np.int32),
+        "leaf": np.zeros((n, height, width), np.int32), "level": np.zeros((n, height, width), np.uint8),
+        "iters": np.zeros((n, height, width), np.uint32), "depth": np.zeros((n, height, width), np.float32),
+        "mask": np.zeros((n, height, width), np.uint8), "pos": np.zeros((n, height, width, 3), np.float32),
+    }
+    a = Aov(*[out[k].ctypes.data for k in ("state", "voxel", "leaf", "level", "iters", "depth", "mask", "pos")])
+    rc = lib().wxe_render_cta_queue(C.addressof(desc), C.addressof(buf), n, width, height, rgba.ctypes.data, C.addressof(a), n_ctas, warps_per_cta)
+    if rc != 0:
+        raise RuntimeError(f"wxe_render_cta_queue failed: {rc}")
+    return rgba, out

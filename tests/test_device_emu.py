@@ -202,3 +202,19 @@ def test_randomized_scenes_and_cameras(seed, bump):
             for name in ("state", "voxel", "leaf", "level", "iters", "mask"):
                 assert np.array_equal(aov[name][0], ref_aov[name]), (case, kind, name, eye, target, mode)
             assert np.array_equal(_bits_nan_canonical(aov["pos"][0]), _bits_nan_canonical(ref_aov["pos"])), (case, kind)
+
+
+@pytest.mark.parametrize("w,h,mode,ncam", [(240, 136, 0, 1), (100, 50, 3, 1), (13, 7, 0, 1), (96, 64, 4, 3)])
+def test_cta_queue_renders_the_same_frames(w, h, mode, ncam):
+    """Whole frames through the ticket protocol + pixel mapping of raycast_persistent_cta (CPU threads in the role of warps): equal
+    to the plain per-pixel emulation, which equals the oracle -- ragged sizes, a shadow-ray mode, a camera batch."""
+    s = scenes.get_scene("icosahedron")
+    cams = ["default", "oblique_a", "oblique_b"][:ncam]
+    sts = [scenes.state_for(*scenes.CAMERAS[c], w, h, mode=mode) for c in cams]
+    rgba, aov = E.render_cta_queue(s.desc(), sts, w, h)
+    ref_rgba, ref_aov, _ = E.render(s.desc(), sts, w, h)
+    assert np.array_equal(rgba, ref_rgba)
+    for k in ("state", "voxel", "leaf", "level", "iters", "mask"):
+        assert np.array_equal(aov[k], ref_aov[k]), k
+    o_rgba, _, _ = s.gpu.render(sts[0], w, h)
+    assert np.array_equal(rgba[0], o_rgba)
