@@ -218,3 +218,28 @@ def test_cta_queue_renders_the_same_frames(w, h, mode, ncam):
         assert np.array_equal(aov[k], ref_aov[k]), k
     o_rgba, _, _ = s.gpu.render(sts[0], w, h)
     assert np.array_equal(rgba[0], o_rgba)
+
+
+@pytest.mark.parametrize("kind", ["torus", "fog"])
+def test_procedural_config_scenes(kind):
+    """BASELINE configs 3 (torus level set, 1/8 scale) and 4 (dense value-noise fog, 1/16 scale) built by the PRODUCT host
+    (set_voxel tree -> compute_sdf -> to_flat): the device code on the CPU against the oracle, from outside and -- for the fog --
+    from inside the volume (long divergent rays), modes 0 / 3 / 4."""
+    import oracle_ffi as O
+    import woxel_b200 as W
+    v = W.VDB345.torus(half=128, major=88.0, minor=31.0, band=2.0) if kind == "torus" else W.VDB345.fog(half=64, tau=0.32)
+    v.compute_sdf()
+    f = v.to_flat(narrow_leaves=False)
+    g = O.gpudata_from_tables(f.origins, f.kids5, f.vals5, f.tab5, f.kids4, f.vals4, f.tab4, f.vals3, f.tab3)
+    w, h = 192, 108
+    cams = [((0.5, 0.5, -320.5), (0.5, 0.5, 0.5)), ((210.0, 140.0, -230.0), (0.0, 0.0, 0.0))]
+    if kind == "fog":
+        cams.append(((3.5, 2.5, 1.5), (60.0, 40.0, 50.0)))
+    for eye, target in cams:
+        for mode in (0, 3, 4):
+            st = scenes.state_for(eye, target, w, h, mode=mode)
+            rgba, aov, _ = E.render(f.desc, st, w, h)
+            ref, ref_aov, _ = g.render(st, w, h)
+            assert np.array_equal(rgba[0], ref), (kind, eye, mode)
+            for k in ("state", "voxel", "leaf", "level", "iters", "mask"):
+                assert np.array_equal(aov[k][0], ref_aov[k]), (kind, eye, mode, k)
