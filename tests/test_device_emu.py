@@ -243,3 +243,34 @@ def test_procedural_config_scenes(kind):
             assert np.array_equal(rgba[0], ref), (kind, eye, mode)
             for k in ("state", "voxel", "leaf", "level", "iters", "mask"):
                 assert np.array_equal(aov[k][0], ref_aov[k]), (kind, eye, mode, k)
+
+
+@pytest.mark.parametrize("what", ["leaf_200", "leaf_70000", "n4_tile_2p18", "n5_tile_2p14"])
+def test_wide_distances_take_the_right_march(what):
+    """Distances that change the layout or the march: a leaf distance of 200 stays in byte bricks and the fast march, 70 000
+    forces u32 bricks and the exact march; an N4 tile of 2^18 cells (size 2^21) or an N5 tile of 2^14 cells (size 2^21) exceed
+    the fast march's 2^20 limit on step sizes -- every case equal to the oracle."""
+    import oracle_ffi as O
+    from woxel_b200.render import make_desc
+    s = scenes.get_scene("single_voxel")
+    t5, t4, t3 = s.tab5.copy(), s.tab4.copy(), s.tab3.copy()
+    k5, k4 = scenes.bits2d(s.kids5), scenes.bits2d(s.kids4)
+    if what == "leaf_200":
+        t3[0, 0] = 200
+    elif what == "leaf_70000":
+        t3[0, 0] = 70000
+    elif what == "n4_tile_2p18":
+        t4[0, int(np.flatnonzero(~k4[0])[3])] = 1 << 18
+    else:
+        t5[0, int(np.flatnonzero(~k5[0])[40])] = 1 << 14
+    desc = make_desc(s.origins, s.kids5, s.vals5, t5, s.kids4, s.vals4, t4, s.vals3, t3)
+    g = O.gpudata_from_tables(s.origins, s.kids5, s.vals5, t5, s.kids4, s.vals4, t4, s.vals3, t3)
+    for eye, target in (((20.5, 20.5, -30.5), (4.0, 4.0, 4.0)), ((300.5, 200.5, -250.5), (5.0, 6.0, 7.0))):
+        st = scenes.state_for(eye, target, 128, 64, mode=0)
+        rgba, aov, stats = E.render(desc, st, 128, 64, stats=True)
+        ref, ref_aov, _ = g.render(st, 128, 64)
+        assert np.array_equal(rgba[0], ref), what
+        for k in ("state", "voxel", "leaf", "level", "iters", "mask"):
+            assert np.array_equal(aov[k][0], ref_aov[k]), (what, k)
+        # the lockstep trace is recorded by the fast march only
+        assert (stats["lane_steps"] > 0) == (what == "leaf_200"), (what, stats["lane_steps"])
