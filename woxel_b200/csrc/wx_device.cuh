@@ -17,6 +17,10 @@
 // operation order (this translation unit is compiled with -fmad=false; fused operations appear
 // only where they are provably equal to the separately rounded sequence).  Results are
 // bit-identical to the CPU oracle, which is how parity is proven (tests/test_parity_gpu.py).
+//
+// WX_HOST_EMU: defined ONLY by tests/emu (test infrastructure), which compiles this header with g++ to check the code below
+// against the oracle on the CPU.  No product build defines it (woxel_b200/csrc/Makefile, tests/test_abi_symbols.py): the
+// library has no CPU path, and wx_init fails without a CUDA device.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
