@@ -49,7 +49,7 @@ extern "C" int wxe_n_stats(void) { return WXE_N_STATS; }
 namespace {
 // The tables wx_tree_upload would send to the GPU, and the launch parameters of a whole-frame, single-shard launch.
 struct EmuScene {
-  std::vector<uint32_t> e5, e4;
+  std::vector<uint32_t> e5, e4, grid, f4;
   std::vector<uint8_t> l3;
   std::vector<int4> origins;
   wx::RenderParams P;
@@ -67,8 +67,11 @@ struct EmuScene {
     // slack so that zero-sized levels have a base address
     e5.push_back(0), e4.push_back(0), l3.push_back(0), origins.push_back(make_int4(0, 0, 0, 0));
     memset(&P, 0, sizeof(P));
-    fill_dev_tree(P.tree, e5.data(), e4.data(), l3.data(), origins.data(), d->n5, d->n4, d->n3, leaf_bits == 8 ? 9 : 11,
-                  fast_march_ok(leaf_bits, max5, max4, max3v), root_grid);
+    const bool fast_ok = fast_march_ok(leaf_bits, max5, max4, max3v);
+    const bool with_grid = world_grid_ok(fast_ok, d->n4, d->n3);
+    if (with_grid) build_grid_tables(d->n5, d->n4, origins, root_grid, e5.data(), e4.data(), grid, f4);
+    fill_dev_tree(P.tree, e5.data(), e4.data(), l3.data(), origins.data(), d->n5, d->n4, d->n3, leaf_bits == 8 ? 9 : 11, fast_ok, root_grid,
+                  with_grid ? grid.data() : nullptr, with_grid ? f4.data() : nullptr);
     P.n_states = n_states;
     P.states = states;
     P.s0 = states[0];

@@ -72,6 +72,7 @@ struct TreeOnDevice {
   uint32_t *e5 = nullptr, *e4 = nullptr;
   uint8_t* l3 = nullptr;
   int4* origins = nullptr;
+  uint32_t *grid = nullptr, *f4 = nullptr;  // world grid and re-encoded N4 tables (wx_device.cuh), derived from e5 / e4 on the device
 };
 
 struct WxTree {
@@ -81,6 +82,7 @@ struct WxTree {
   int16_t root_grid[64];      // root cells of [-8192, 8192)^3 (DevTree::root_grid)
   uint32_t leaf_shift = 9;    // log2(bytes per leaf brick)
   bool fast_ok = true;        // every step size < 2^20: the fast march applies
+  bool grid_ok = true;        // ... and the index bases of the world grid fit 32 bits: march_grid applies
   WxTreeInfo info{};
 };
 
@@ -101,6 +103,67 @@ static int fail_cuda(WxContext* ctx, cudaError_t e, const char* where) {
     cudaError_t e_ = (call);                                    \
     if (e_ != cudaSuccess) return fail_cuda((ctx), e_, #call);  \
   } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// World grid + re-encoded N4 tables of one replica, derived on the device from the e5 / e4 tables it already holds (uploaded
+// by wx_tree_upload or written by the SDF sweep of wx_tree_build).  Same formulas as the host version in wx_pack.h
+// (build_grid_tables), through the helpers of wx_device.cuh.
+// ---------------------------------------------------------------------------------------------
+namespace {
+struct RootGrid {
+  int16_t v[64];
+};
+__global__ void n4_origins_kernel(const uint32_t* __restrict__ e5, const int4* __restrict__ origins, uint32_t n5, uint32_t* __restrict__ o4) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)n5 * 32768u) return;
+  const uint32_t e = e5[i];
+  if (!(e & kChildFlag)) return;
+  const int4 o = origins[i >> 15];
+  const uint32_t s = (uint32_t)i & 32767u;
+  uint32_t* d = o4 + (size_t)(e & ~kChildFlag) * 3u;
+  d[0] = (uint32_t)o.x + (s >> 10) * 128u, d[1] = (uint32_t)o.y + ((s >> 5) & 31u) * 128u, d[2] = (uint32_t)o.z + (s & 31u) * 128u;
+}
+__global__ void build_grid_kernel(const uint32_t* __restrict__ e5, const __grid_constant__ RootGrid rg, uint32_t* __restrict__ grid) {
+  const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;  // the 128^3 cells of the cube (the pads keep the memset's kEntrySlow)
+  if (c >= kGS * kGS2) return;
+  grid[(size_t)kGridPad + c] = grid_cell_entry(c >> 14, (c >> 7) & 127u, c & 127u, rg.v, e5);
+}
+__global__ void build_f4_kernel(const uint32_t* __restrict__ e4, const uint32_t* __restrict__ o4, uint32_t n4, uint32_t* __restrict__ f4) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)n4 * 4096u) return;
+  const uint32_t e = e4[i];
+  const uint32_t* o = o4 + (i >> 12) * 3u;
+  const uint32_t s = (uint32_t)i & 4095u;
+  f4[i] = (e & kChildFlag) ? grid_word3(e & ~kChildFlag, o[0] + (s >> 8) * 8u, o[1] + ((s >> 4) & 15u) * 8u, o[2] + (s & 15u) * 8u) : e;
+}
+}  // namespace
+
+// Current device = the replica's device; everything is enqueued on `stream` (the scratch is freed in stream order).
+static cudaError_t build_grid_on_device(uint32_t*& grid, uint32_t*& f4, const uint32_t* e5, const uint32_t* e4, const int4* origins,
+                                        uint32_t n5, uint32_t n4, const int16_t root_grid[64], cudaStream_t stream) {
+  cudaError_t e = cudaMalloc(&grid, kGridCells * 4);
+  if (e == cudaSuccess) e = cudaMalloc(&f4, (size_t)n4 * 4096u * 4u + 256);
+  uint32_t* o4 = nullptr;
+  if (e == cudaSuccess) e = cudaMallocAsync((void**)&o4, (size_t)n4 * 12u + 256, stream);
+  if (e != cudaSuccess) return e;
+  e = cudaMemsetAsync(grid, 0x02, kGridCells * 4, stream);  // kEntrySlow everywhere
+  if (e == cudaSuccess && n5) {
+    n4_origins_kernel<<<(unsigned)(((size_t)n5 * 32768u + 255) / 256), 256, 0, stream>>>(e5, origins, n5, o4);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) {
+    RootGrid rg;
+    memcpy(rg.v, root_grid, sizeof(rg.v));
+    build_grid_kernel<<<kGS * kGS2 / 256, 256, 0, stream>>>(e5, rg, grid);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess && n4) {
+    build_f4_kernel<<<(unsigned)(((size_t)n4 * 4096u + 255) / 256), 256, 0, stream>>>(e4, o4, n4, f4);
+    e = cudaGetLastError();
+  }
+  const cudaError_t fe = cudaFreeAsync(o4, stream);
+  return e != cudaSuccess ? e : fe;
+}
 
 extern "C" int wx_abi_version(void) { return WX_ABI_VERSION; }
 
@@ -238,11 +301,13 @@ static WxTree* new_tree(WxContext* ctx, const WxTreeDesc* d, uint32_t leaf_bits,
   t->leaf_shift = leaf_bits == 8 ? 9 : 11;
   // the fast march needs byte leaves and every step size below 2^20 (wx_device.cuh); anything else takes the exact march
   t->fast_ok = fast_march_ok(leaf_bits, max5, max4, max3v);
+  t->grid_ok = world_grid_ok(t->fast_ok, d->n4, d->n3);
   t->info.n5 = d->n5, t->info.n4 = d->n4, t->info.n3 = d->n3;
   t->info.leaf_bits = leaf_bits;
   t->info.max_dist[0] = max5, t->info.max_dist[1] = max4, t->info.max_dist[2] = max3v;
   t->info.n_devices = (uint32_t)ctx->dev.size();
-  t->info.device_bytes = ((size_t)d->n5 * 32768 + (size_t)d->n4 * 4096) * 4 + ((size_t)d->n3 << t->leaf_shift) + t->origins.size() * sizeof(int4);
+  t->info.device_bytes = ((size_t)d->n5 * 32768 + (size_t)d->n4 * 4096) * 4 + ((size_t)d->n3 << t->leaf_shift) + t->origins.size() * sizeof(int4) +
+                         (t->grid_ok ? kGridCells * 4 + (size_t)d->n4 * 4096 * 4 : 0);
   t->on.resize(ctx->dev.size());
   return t;
 }
@@ -287,6 +352,7 @@ extern "C" int wx_tree_upload(WxContext* ctx, const WxTreeDesc* d, WxTree** out)
     if (!l3.empty()) WX_CUDA(ctx, cudaMemcpyAsync(o.l3, l3.data(), l3.size(), cudaMemcpyHostToDevice, s.stream));
     if (!t->origins.empty())
       WX_CUDA(ctx, cudaMemcpyAsync(o.origins, t->origins.data(), t->origins.size() * sizeof(int4), cudaMemcpyHostToDevice, s.stream));
+    if (t->grid_ok) WX_CUDA(ctx, build_grid_on_device(o.grid, o.f4, o.e5, o.e4, o.origins, d->n5, d->n4, t->root_grid, s.stream));
     return WX_OK;
   };
   for (int i = 0; i < (int)ctx->dev.size(); ++i) {
@@ -397,6 +463,10 @@ extern "C" int wx_tree_build(WxContext* ctx, const WxTreeDesc* d, WxTree** out, 
     e = cudaMemcpyAsync(first.origins, t->origins.data(), t->origins.size() * sizeof(int4), cudaMemcpyHostToDevice, d0.stream);
     if (e != cudaSuccess) return bail(e, "wx_tree_build: origins");
   }
+  if (t->grid_ok) {
+    e = build_grid_on_device(t->on[0].grid, t->on[0].f4, first.e5, first.e4, first.origins, d->n5, d->n4, t->root_grid, d0.stream);
+    if (e != cudaSuccess) return bail(e, "wx_tree_build: world grid");
+  }
   // replicate read-only on the other devices of the context (peer copies over NVLink)
   for (size_t i = 1; i < ctx->dev.size(); ++i) {
     DeviceSlot& s = ctx->dev[i];
@@ -406,12 +476,18 @@ extern "C" int wx_tree_build(WxContext* ctx, const WxTreeDesc* d, WxTree** out, 
     if (e == cudaSuccess) e = cudaMalloc(&o.e4, s4 * 4 + 256);
     if (e == cudaSuccess) e = cudaMalloc(&o.l3, s3 + 256);
     if (e == cudaSuccess) e = cudaMalloc(&o.origins, t->origins.size() * sizeof(int4) + 256);
+    if (e == cudaSuccess && t->grid_ok) e = cudaMalloc(&o.grid, kGridCells * 4);
+    if (e == cudaSuccess && t->grid_ok) e = cudaMalloc(&o.f4, s4 * 4 + 256);
     if (e == cudaSuccess) e = cudaSetDevice(d0.id);
     if (e == cudaSuccess && s5) e = cudaMemcpyPeerAsync(o.e5, s.id, first.e5, d0.id, s5 * 4, d0.stream);
     if (e == cudaSuccess && s4) e = cudaMemcpyPeerAsync(o.e4, s.id, first.e4, d0.id, s4 * 4, d0.stream);
     if (e == cudaSuccess && s3) e = cudaMemcpyPeerAsync(o.l3, s.id, first.l3, d0.id, s3, d0.stream);
     if (e == cudaSuccess && !t->origins.empty())
       e = cudaMemcpyPeerAsync(o.origins, s.id, first.origins, d0.id, t->origins.size() * sizeof(int4), d0.stream);
+    if (e == cudaSuccess && t->grid_ok) {
+      e = cudaMemcpyPeerAsync(o.grid, s.id, t->on[0].grid, d0.id, kGridCells * 4, d0.stream);
+      if (e == cudaSuccess && s4) e = cudaMemcpyPeerAsync(o.f4, s.id, t->on[0].f4, d0.id, s4 * 4, d0.stream);
+    }
     if (e != cudaSuccess) return bail(e, "wx_tree_build: replicate");
   }
   e = cudaStreamSynchronize(d0.stream);
@@ -426,11 +502,14 @@ extern "C" int wx_tree_free(WxContext* ctx, WxTree* tree) {
   WxContext* c = ctx ? ctx : tree->ctx;
   for (size_t i = 0; i < tree->on.size() && c && i < c->dev.size(); ++i) {
     (void)cudaSetDevice(c->dev[i].id);
+    (void)cudaDeviceSynchronize();  // launches of wx_render_device (any stream) may still be reading the tables
     TreeOnDevice& o = tree->on[i];
     if (o.e5) (void)cudaFree(o.e5);
     if (o.e4) (void)cudaFree(o.e4);
     if (o.l3) (void)cudaFree(o.l3);
     if (o.origins) (void)cudaFree(o.origins);
+    if (o.grid) (void)cudaFree(o.grid);
+    if (o.f4) (void)cudaFree(o.f4);
   }
   delete tree;
   return WX_OK;
@@ -454,10 +533,11 @@ static int launch_on(WxContext* ctx, int dev_i, const WxTree* tree, const WxStat
                      bool states_on_device = false) {
   DeviceSlot& s = ctx->dev[dev_i];
   const TreeOnDevice& o = tree->on[dev_i];
+  WxState* launch_states = nullptr;
   RenderParams P;
   memset(&P, 0, sizeof(P));
   fill_dev_tree(P.tree, o.e5, o.e4, o.l3, o.origins, tree->info.n5, tree->info.n4, tree->info.n3, tree->leaf_shift, tree->fast_ok,
-                tree->root_grid);
+                tree->root_grid, o.grid, o.f4);
   P.n_states = n_states;
   P.width = width, P.height = height;
   P.rgba = reinterpret_cast<uchar4*>(rgba_dev);
@@ -470,15 +550,18 @@ static int launch_on(WxContext* ctx, int dev_i, const WxTree* tree, const WxStat
     P.s0 = states[0];
   } else {
     if (!states_on_device) {
-      if (s.states_cap < n_states) {
-        if (s.d_states) (void)cudaFree(s.d_states);
-        s.d_states = nullptr, s.states_cap = 0;
-        WX_CUDA(ctx, cudaMalloc(&s.d_states, (size_t)n_states * sizeof(WxState)));
-        s.states_cap = n_states;
+      // The batch of THIS launch, allocated and freed in stream order: asynchronous wx_render_device calls on different
+      // streams never share a states buffer (s.d_states is only used by the blocking wx_render, which uploads it once).
+      WX_CUDA(ctx, cudaMallocAsync((void**)&launch_states, (size_t)n_states * sizeof(WxState), stream));
+      cudaError_t ce = cudaMemcpyAsync(launch_states, states, (size_t)n_states * sizeof(WxState), cudaMemcpyHostToDevice, stream);
+      if (ce != cudaSuccess) {
+        (void)cudaFreeAsync(launch_states, stream);
+        return fail_cuda(ctx, ce, "render: states upload");
       }
-      WX_CUDA(ctx, cudaMemcpyAsync(s.d_states, states, (size_t)n_states * sizeof(WxState), cudaMemcpyHostToDevice, stream));
+      P.states = launch_states;
+    } else {
+      P.states = s.d_states;
     }
-    P.states = s.d_states;
   }
   const uint32_t cam1 = ncam > n_states - cam0 ? n_states : cam0 + ncam;
   uint32_t total_launches = 0;
@@ -493,10 +576,15 @@ static int launch_on(WxContext* ctx, int dev_i, const WxTree* tree, const WxStat
     P.row_base = row0, P.row_end = row1;
     uint32_t l = 0;
     uint32_t* counter = s.counters + (s.counter_next++ % kCounterRing);
-    WX_CUDA(ctx, launch_raycast(P, e - b, mode, stream, &l, counter, s.resident_ctas));
+    const cudaError_t le = launch_raycast(P, e - b, mode, stream, &l, counter, s.resident_ctas);
+    if (le != cudaSuccess) {
+      if (launch_states) (void)cudaFreeAsync(launch_states, stream);
+      return fail_cuda(ctx, le, "launch_raycast");
+    }
     total_launches += l;
     b = e;
   }
+  if (launch_states) WX_CUDA(ctx, cudaFreeAsync(launch_states, stream));
   *launches_out = total_launches;
   return WX_OK;
 }
@@ -626,7 +714,7 @@ static int render_distributed(WxContext* ctx, const WxTree* tree, const WxState*
     s.events_pending = true;
     if (n_chunks == 1) {  // kernel and copy in stream order, nothing to overlap (and the fewest host calls)
       uint32_t l = 0;
-      int rc = launch_on(ctx, i, tree, states, n_states, width, height, local, nullptr, &sh, s.stream, &l);
+      int rc = launch_on(ctx, i, tree, states, n_states, width, height, local, nullptr, &sh, s.stream, &l, 0, 0xffffffffu, 0, 0, n_states > 1);
       if (rc) return rc;
       *launches += l;
       WX_CUDA(ctx, cudaEventRecord(s.ev1, s.stream));
@@ -828,12 +916,9 @@ extern "C" int wx_render(WxContext* ctx, const WxTree* tree, const WxState* stat
     }
     for (int i = 1; i < ndev; ++i) {  // device 0's stream waits for the peers' stores
       WX_CUDA(ctx, cudaSetDevice(ctx->dev[i].id));
-      cudaEvent_t done;
-      WX_CUDA(ctx, cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
-      WX_CUDA(ctx, cudaEventRecord(done, ctx->dev[i].stream));
+      WX_CUDA(ctx, cudaEventRecord(ctx->dev[i].join[0], ctx->dev[i].stream));  // the slot's own event (created in wx_init)
       WX_CUDA(ctx, cudaSetDevice(d0.id));
-      WX_CUDA(ctx, cudaStreamWaitEvent(d0.stream, done, 0));
-      WX_CUDA(ctx, cudaEventDestroy(done));
+      WX_CUDA(ctx, cudaStreamWaitEvent(d0.stream, ctx->dev[i].join[0], 0));
     }
     WX_CUDA(ctx, cudaSetDevice(d0.id));
   }

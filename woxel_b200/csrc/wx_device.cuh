@@ -68,6 +68,9 @@ struct DevTree {
   // not fit: scan origins), else the N5 index, | kRootBeyond when the cell reaches outside the world (its origin has a
   // component outside [-4096, 0]), where the march must test the bounds.  Outside the grid: scan origins.
   int16_t root_grid[64];
+  // World grid (the march's usual top level, see "World grid" below); grid == nullptr when the tree does not qualify.
+  const uint32_t* __restrict__ grid;  // kGridCells entries
+  const uint32_t* __restrict__ f4;    // re-encoded N4 tables: the child entries of e4 as index bases (grid_word3)
 #ifdef WX_ROOT_PTRS
   // A/B variant (measured 0.7 % SLOWER than the int16 cells + address arithmetic, profiles/r1_variants_h.txt; not the default):
   // the same cells as ready-made N5 table addresses of THIS replica: kRootPtrNone = no N5, kRootPtrScan = scan the
@@ -77,6 +80,55 @@ struct DevTree {
 #endif
 };
 constexpr uint64_t kRootPtrNone = 2ull, kRootPtrScan = 6ull;
+
+// ---------------------------------------------------------------------------------------------
+// World grid: the top level the march normally reads (march_grid).  The reference finds the N5 of a position by scanning
+// origins[] and then indexes that N5's table (raycast.comp.wgsl:398-444).  Every position a ray can visit while it is inside
+// the +-4096 world lies in [-8192 - 1, 8192 + 1)^3 as long as no step is longer than 4096, so ONE dense table of 128-voxel
+// cells over that cube replaces the root lookup and all N5 tables: 128^3 cells + a pad of one cell row/plane on either end,
+// 8.5 MB, of which only the 64^3 in-world cells (1 MB, the size of 8 N5 tables) are ever hot.
+//   entry, in-world cell of an existing N5 : the N5's slot -- tile: f32 bits of `size` (0.0f = active tile) as in e5;
+//                                             child: word4 (below)
+//          in-world cell without an N5     : f32 bits of 4096.0f (dist 1 at level 0, :411)
+//          cell outside the world, no N5   : kEntryVoid -- the lookup there is "dist 1 at level 0" and the bounds test of
+//                                             :100-103 follows: the ray ends out of bounds unless it sits exactly on +4096
+//          anything else                   : kEntrySlow -- a cell outside the world inside some N5 (a hit is possible before
+//                                             the bounds test), a tile larger than 4096, the pads.  The march then hands the
+//                                             ray to the generic loop (march_fast from the current state), which knows all that.
+// Tile sizes are positive, so bit 31 marks a child (as in e5 / e4); kEntrySlow is a float below 1 that no tile can be.
+// Child words are INDEX BASES, not node numbers: with biased voxel coordinates (x, y, z) the N4 slot of a position is
+//   f4[(x >> 3) * 256 + (y >> 3) * 16 + (z >> 3) + (word4 << 4)],   word4 = kChildFlag | (n4 * 4096 - C4(N4 origin)) >> 4   (mod 2^32)
+// and the voxel of a leaf l3[x * 64 + y * 8 + z + (word3 << 3)], word3 = kChildFlag | (n3 * 512 - C3(leaf origin)) >> 3: no masking of
+// the coordinates, no 64-bit node pointer in the cursor.  C4 is a multiple of 16 and C3 of 8, and the shift that undoes the
+// division also drops the flag bit (it is part of the index add: one LEA).
+// ---------------------------------------------------------------------------------------------
+constexpr uint32_t kGS = 128u, kGS2 = kGS * kGS;
+constexpr uint32_t kGridPad = kGS2 + kGS + 1u;
+constexpr size_t kGridCells = (size_t)kGS * kGS2 + 2u * (size_t)kGridPad;
+// cell index of biased coordinates: (x >> 7) * kGS2 + (y >> 7) * kGS + (z >> 7) + kGridK   (mod 2^32)
+constexpr uint32_t kGridK = kGridPad - ((kBias >> 7) - 64u) * (kGS2 + kGS + 1u);
+constexpr uint32_t kEntrySlow = 0x02020202u;  // what cudaMemset(.., 0x02, ..) writes: 9.6e-38f
+constexpr uint32_t kEntryVoid = 0x01010101u;  // 2.4e-38f
+constexpr float kGridMaxSize = 4096.f;
+constexpr uint32_t kGridMaxN3 = (1u << 23) - 1u, kGridMaxN4 = (1u << 20) - 1u;  // index bases must fit 32 bits
+
+__host__ __device__ inline uint32_t grid_word4(uint32_t n4, uint32_t ox, uint32_t oy, uint32_t oz) {  // biased N4 origin
+  return kChildFlag | ((n4 * 4096u - ((ox >> 3) * 256u + (oy >> 3) * 16u + (oz >> 3))) >> 4);
+}
+__host__ __device__ inline uint32_t grid_word3(uint32_t n3, uint32_t ox, uint32_t oy, uint32_t oz) {  // biased leaf origin
+  return kChildFlag | ((n3 * 512u - (ox * 64u + oy * 8u + oz)) >> 3);
+}
+// Entry of cell (cx, cy, cz) of the 128^3 cube: cell coordinate = true coordinate / 128 + 64; in-world cells are [32, 96)^3.
+__host__ __device__ inline uint32_t grid_cell_entry(uint32_t cx, uint32_t cy, uint32_t cz, const int16_t* root_grid, const uint32_t* e5) {
+  const int v = (int)root_grid[(cx >> 5) * 16u + (cy >> 5) * 4u + (cz >> 5)];  // (true >> 12) + 2 == cell >> 5
+  if (((cx - 32u) | (cy - 32u) | (cz - 32u)) >= 64u) return v == kRootNone ? kEntryVoid : kEntrySlow;  // outside the world
+  if (v == kRootNone) return 0x45800000u;                                       // 4096.0f
+  if (v < 0 || (v & kRootBeyond)) return kEntrySlow;
+  const uint32_t e = e5[(size_t)(v & kRootIndexMask) * 32768u + (((cx & 31u) << 10) | ((cy & 31u) << 5) | (cz & 31u))];
+  if (e & kChildFlag)
+    return grid_word4(e & ~kChildFlag, (cx - 64u) * 128u + kBias, (cy - 64u) * 128u + kBias, (cz - 64u) * 128u + kBias);
+  return e > 0x45800000u ? kEntrySlow : e;  // a tile larger than 4096 (positive floats order like their bit patterns)
+}
 
 struct AovPtrs {
   uint8_t* state;
@@ -571,11 +623,21 @@ struct FastRay {
   }
 };
 
-__device__ __forceinline__ HitOut march_fast(const DevTree& T, V3 src, V3 dir, V3 idir) {
+// The generic fast march: any tree with byte leaves and sizes below 2^20, any start position below 2^21, N5s anywhere.  Since
+// march_grid took over the usual rays this is the out-of-line fallback: rays that start beyond the world grid, trees that do
+// not qualify for it, and rays march_grid hands over when they reach a cell it does not decide itself (`resume`: iteration
+// index, and tMax / its minimum of the step before, from which the mask is derived if the ray ends at once).
+static __device__ __noinline__ HitOut march_fast(const DevTree& T, V3 src, V3 dir, V3 idir, uint32_t i0 = 0u, float ltx = 1.f,
+                                                 float lty = 1.f, float ltz = 1.f, float lt = 0.f) {
   FastRay r;
   r.init(src, dir, idir);
+  r.i = i0, r.ltx = ltx, r.lty = lty, r.ltz = ltz, r.lt = lt;
+  if (r.i & 1u) {  // the loop below counts in pairs (kMaxRaySteps is even)
+    if (r.step(T)) return r.result(T, true);
+    r.i += 1u;
+  }
   // Two steps per trip: the cursor's last-voxel registers alternate instead of being copied and the step budget
-  // (kMaxRaySteps is even) is tested once per trip.
+  // is tested once per trip.
   for (; r.i < kMaxRaySteps; r.i += 2u) {
     if (r.step(T)) break;
     if (r.step(T)) {
@@ -586,6 +648,152 @@ __device__ __forceinline__ HitOut march_fast(const DevTree& T, V3 src, V3 dir, V
   return r.result(T, r.i < kMaxRaySteps);  // a break leaves i below the budget
 }
 
+// ---------------------------------------------------------------------------------------------
+// march_grid: hdda_ray over the world grid (see "World grid" at the top).  The arithmetic of a step is FastRay's, value for
+// value; what differs is the lookup: no root level, one 32-bit index base per level instead of a node pointer, coordinates
+// never masked.  Preconditions (grid_ray_ok): those of the fast march, a tree with a world grid, and a start position inside
+// (-8192, 8192)^3.  From an in-world position no step is longer than 4096 (larger tiles and everything outside the world are
+// kEntrySlow cells), so every lookup stays inside the grid or its pads; a ray that meets a slow cell leaves for march_fast.
+// ---------------------------------------------------------------------------------------------
+struct VoxelId {
+  uint32_t x, y, z;  // biased voxel coordinates
+};
+
+__device__ __forceinline__ VoxelId opaque_copy(const VoxelId& s) {
+  VoxelId d;
+#ifndef WX_HOST_EMU
+  asm volatile("mov.b32 %0, %3;\n\tmov.b32 %1, %4;\n\tmov.b32 %2, %5;" : "=r"(d.x), "=r"(d.y), "=r"(d.z) : "r"(s.x), "r"(s.y), "r"(s.z));
+#else
+  d = s;
+#endif
+  return d;
+}
+
+struct GridRay {
+  f32x2 pxy, dxy, ixy, s01xy;
+  float pz, dz, iz, s01z;
+  float ndx, ndy, ndz;
+  float ltx, lty, ltz, lt;
+  float size;                // last lookup: 0 = hit, a value in (0, 1) = slow cell, else the step size
+  uint32_t dbits;            // 0: w4 and w3 valid (last lookup ended in a leaf), 8: w4 valid, 128: neither
+  uint32_t w4, w3;           // index bases of the N4 table / leaf brick the cursor is in (grid_word4 << 4 / grid_word3 << 3)
+  uint32_t i;
+
+  __device__ __forceinline__ void init(V3 src, V3 dir, V3 idir) {
+    pxy = pk(src.x, src.y), pz = src.z;
+    dxy = pk(dir.x, dir.y), dz = dir.z;
+    ixy = pk(idir.x, idir.y), iz = idir.z;
+    s01xy = pk(keep(dir.x < 0.f ? 0.f : 1.f), keep(dir.y < 0.f ? 0.f : 1.f));
+    s01z = keep(dir.z < 0.f ? 0.f : 1.f);
+    ndx = keep(dir.x < 0.f ? -4e-4f : 4e-4f), ndy = keep(dir.y < 0.f ? -4e-4f : 4e-4f), ndz = keep(dir.z < 0.f ? -4e-4f : 4e-4f);
+    ltx = 1.f, lty = 1.f, ltz = 1.f, lt = 0.f;
+    size = 1.f;
+    dbits = 128u, w4 = 0u, w3 = 0u;
+    i = 0;
+  }
+
+  // One iteration of hdda_ray's loop body (:90-122) without the counter: `last` is the voxel of the lookup before, `cur`
+  // receives this one's (the caller alternates two VoxelIds, so nothing is copied).  Returns true when the ray left the
+  // loop: a hit (size == 0) or a slow cell (0 < size < 1).
+  __device__ __forceinline__ bool step(const DevTree& T, const VoxelId& last, VoxelId& cur) {
+    const f32x2 txy = add2_rd(pxy, bc(kMagic));
+    const float tz = __fadd_rd(pz, kMagic);
+    const uint32_t x = (uint32_t)txy, y = (uint32_t)(txy >> 32), z = __float_as_uint(tz);
+    const uint32_t dv = ((x ^ last.x) | dbits) | (y ^ last.y) | (z ^ last.z);
+    cur.x = x, cur.y = y, cur.z = z;
+    // lookup L(pos): from the deepest node the cursor still holds
+    uint32_t lvl = dv >= 128u ? 5u : (dv >= 8u ? 4u : 3u);  // level whose table is read next; 0 = walk finished
+    if (lvl == 5u) {
+      const uint32_t e = __ldg(T.grid + (uint32_t)((x >> 7) * kGS2 + (y >> 7) * kGS + (z >> 7) + kGridK));
+      if ((int32_t)e >= 0) dbits = 128u, size = __uint_as_float(e), lvl = 0u;
+      else w4 = e << 4, lvl = 4u;  // the shift drops the flag; an operation here (not a copy) lets the load target `size` directly
+    }
+    if (lvl == 4u) {
+      const uint32_t e = __ldg(T.f4 + (uint32_t)((x >> 3) * 256u + (y >> 3) * 16u + (z >> 3) + w4));
+      if ((int32_t)e >= 0) dbits = 8u, size = __uint_as_float(e), lvl = 0u;
+      else w3 = e << 3, lvl = 3u;
+    }
+    if (lvl == 3u) {
+      dbits = 0u;
+      size = u32_to_float(__ldg(T.l3 + (uint32_t)(x * 64u + y * 8u + z + w3)));
+    }
+    if (size == 0.f || size >= 1.f) WX_EMU_STEP(dv >= 128u ? 128u : dv, dbits);  // (tests/emu only; a slow cell's lookup is redone, and traced, by march_fast)
+    if (size < 1.f) return true;  // hit, or a slow cell
+    const float r = rcp_approx(size);
+    const float hr = 0.5f * r;
+    const f32x2 xfxy = add2(txy, bc(-kMagic));                         // float(floor(p)), exact
+    const float xfz = tz - kMagic;
+    const f32x2 qxy = add2_rd(fma2(xfxy, bc(r), bc(hr)), bc(kMagic));  // kMagic + floor(p / size)
+    const float qz = __fadd_rd(fmaf(xfz, r, hr), kMagic);
+    const f32x2 kxy = add2(qxy, bc(-kMagic));                          // see FastRay::step for the argument
+    const float kz = qz - kMagic;
+    const f32x2 nmxy = fma2(kxy, bc(size), pk(-lo(pxy), -hi(pxy)));    // -modulo_vec3f(p, size)
+    const float nmz = fmaf(kz, size, -pz);
+    const f32x2 tmxy = mul2(ixy, fma2(bc(size), s01xy, nmxy));         // tMax
+    const float tmz = iz * fmaf(size, s01z, nmz);
+    ltx = lo(tmxy), lty = hi(tmxy), ltz = tmz;
+    lt = fminf(fminf(ltx, lty), ltz);
+    const f32x2 axy = mul2(bc(lt), dxy);
+    float px = lo(pxy) + lo(axy), py = hi(pxy) + hi(axy);
+    pz = pz + lt * dz;
+    if (ltx == lt) px += ndx;
+    if (lty == lt) py += ndy;
+    if (ltz == lt) pz += ndz;
+    pxy = pk(px, py);
+    return false;
+  }
+};
+
+__device__ __forceinline__ HitOut march_grid(const DevTree& T, V3 src, V3 dir, V3 idir) {
+  GridRay r;
+  r.init(src, dir, idir);
+  // Two steps per trip over two alternating VoxelIds: nothing is copied inside the loop, and the step budget (kMaxRaySteps
+  // is even) is tested once per trip.  The copies at the exits are opaque so that the compiler does not merge a and b.
+  VoxelId a{0u, 0u, 0u}, b{0u, 0u, 0u}, v;
+  for (;;) {
+    if (r.step(T, a, b)) {
+      v = opaque_copy(b);
+      break;
+    }
+    if (r.step(T, b, a)) {
+      v = opaque_copy(a), r.i += 1u;
+      break;
+    }
+    r.i += 2u;
+    if (r.i >= kMaxRaySteps) {
+      v = opaque_copy(a);
+      break;
+    }
+  }
+  const bool ended = r.i < kMaxRaySteps;
+  const V3 p = V3{lo(r.pxy), hi(r.pxy), r.pz};
+  HitOut out;
+  out.p = p;
+  out.mask = (uint32_t)(r.ltx == r.lt) | ((uint32_t)(r.lty == r.lt) << 1) | ((uint32_t)(r.ltz == r.lt) << 2);
+  out.i = r.i;
+  if (ended && r.size != 0.f) {
+    // the usual end of a ray that misses: a cell outside the world without an N5 -- dist 1 at level 0 (:411), then out of bounds (:100-103)
+    if (__float_as_uint(r.size) == kEntryVoid && out_of_bounds(p.x, p.y, p.z)) {
+      out.state = 1u, out.level = 0u, out.n3 = 0u;
+      WX_EMU_STEP(128u, kNoCache);  // (tests/emu only: this lookup read the grid and ended at level 0)
+      return out;
+    }
+    return march_fast(T, p, dir, idir, r.i, r.ltx, r.lty, r.ltz, r.lt);  // slow cell: redo this lookup there
+  }
+  out.state = ended ? 0u : 2u;
+  out.level = r.dbits == 0u ? 3u : (r.dbits == 8u ? 2u : 1u);
+  // a ray that ran out of steps on an in-world cell without an N5 ended at level 0 (the grid stores that cell as a 4096 tile)
+  if (!ended && r.dbits == 128u && find_root(T, v.x, v.y, v.z) < 0) out.level = 0u;
+  out.n3 = out.level == 3u ? (r.w3 + ((v.x & ~7u) * 64u + (v.y & ~7u) * 8u + (v.z & ~7u))) >> 9 : 0u;
+  return out;
+}
+
+// march_grid applies to this ray.
+__device__ __forceinline__ bool grid_ray_ok(const DevTree& T, V3 src, V3 idir) {
+  return T.grid != nullptr && fmaxf(fmaxf(fabsf(idir.x), fabsf(idir.y)), fabsf(idir.z)) < 1e30f &&
+         fmaxf(fmaxf(fabsf(src.x), fabsf(src.y)), fabsf(src.z)) < 8192.f;
+}
+
 // The fast march applies to this ray (see its preconditions).
 __device__ __forceinline__ bool fast_ray_ok(const DevTree& T, V3 src, V3 idir) {
   return T.fast_ok && fmaxf(fmaxf(fabsf(idir.x), fabsf(idir.y)), fabsf(idir.z)) < 1e30f &&
@@ -594,6 +802,9 @@ __device__ __forceinline__ bool fast_ray_ok(const DevTree& T, V3 src, V3 idir) {
 
 __device__ __forceinline__ HitOut hdda_ray(const DevTree& T, V3 src, V3 dir) {
   const V3 idir = V3{1.f / dir.x, 1.f / dir.y, 1.f / dir.z};
+#ifndef WX_NO_GRID
+  if (grid_ray_ok(T, src, idir)) return march_grid(T, src, dir, idir);
+#endif
   if (fast_ray_ok(T, src, idir)) return march_fast(T, src, dir, idir);
   return march_exact(T, src, dir);
 }

@@ -146,10 +146,42 @@ static inline bool fast_march_ok(uint32_t leaf_bits, uint32_t max5, uint32_t max
          (double)max3v < (double)kFastMaxSize;
 }
 
-// The kernel's view of one replica of the tree.
+// The world grid applies (wx_device.cuh): the fast march's conditions, and index bases that fit 32 bits.
+static inline bool world_grid_ok(bool fast_ok, uint32_t n4, uint32_t n3) { return fast_ok && n4 <= kGridMaxN4 && n3 <= kGridMaxN3; }
+
+// Host version of the world grid and the re-encoded N4 tables (the library derives the same on the device from the tables it
+// has just uploaded or swept, build_grid_kernel / build_f4_kernel in wx_api.cu, through the same helpers of wx_device.cuh).
+// o4 (scratch): biased origin of every N4, from the N5 slot that points to it.
+static inline void build_grid_tables(uint32_t n5, uint32_t n4, const std::vector<int4>& origins, const int16_t root_grid[64],
+                                     const uint32_t* e5, const uint32_t* e4, std::vector<uint32_t>& grid, std::vector<uint32_t>& f4) {
+  std::vector<uint32_t> o4((size_t)n4 * 3u, 0u);
+  for (uint32_t i = 0; i < n5; ++i)
+    for (uint32_t s = 0; s < 32768u; ++s) {
+      const uint32_t e = e5[(size_t)i * 32768u + s];
+      if (!(e & kChildFlag)) continue;
+      uint32_t* o = o4.data() + (size_t)(e & ~kChildFlag) * 3u;
+      o[0] = (uint32_t)origins[i].x + (s >> 10) * 128u, o[1] = (uint32_t)origins[i].y + ((s >> 5) & 31u) * 128u, o[2] = (uint32_t)origins[i].z + (s & 31u) * 128u;
+    }
+  grid.assign(kGridCells, kEntrySlow);  // the pads stay slow
+  parallel_for((size_t)kGS * kGS2, [&](size_t c) {
+    grid[(size_t)kGridPad + c] = grid_cell_entry((uint32_t)(c >> 14), (uint32_t)((c >> 7) & 127u), (uint32_t)(c & 127u), root_grid, e5);
+  });
+  f4.assign((size_t)n4 * 4096u + 1u, 0u);
+  parallel_for(n4, [&](size_t node) {
+    const uint32_t* o = o4.data() + node * 3u;
+    for (uint32_t s = 0; s < 4096u; ++s) {
+      const uint32_t e = e4[node * 4096u + s];
+      f4[node * 4096u + s] = (e & kChildFlag) ? grid_word3(e & ~kChildFlag, o[0] + (s >> 8) * 8u, o[1] + ((s >> 4) & 15u) * 8u, o[2] + (s & 15u) * 8u) : e;
+    }
+  });
+}
+
+// The kernel's view of one replica of the tree.  grid / f4: nullptr when the tree has no world grid.
 static inline void fill_dev_tree(DevTree& T, const uint32_t* e5, const uint32_t* e4, const uint8_t* l3, const int4* origins, uint32_t n5,
-                                 uint32_t n4, uint32_t n3, uint32_t leaf_shift, bool fast_ok, const int16_t root_grid[64]) {
+                                 uint32_t n4, uint32_t n3, uint32_t leaf_shift, bool fast_ok, const int16_t root_grid[64],
+                                 const uint32_t* grid = nullptr, const uint32_t* f4 = nullptr) {
   T.e5 = e5, T.e4 = e4, T.l3 = l3, T.origins_g = origins;
+  T.grid = (grid && f4) ? grid : nullptr, T.f4 = f4;
   // a child entry keeps its flag bit: node = adj + entry * node_bytes, adj = base - 2^31 * node_bytes
   T.e4_adj = reinterpret_cast<const char*>(e4) - ((uint64_t)kChildFlag << 14);
   T.l3_adj = reinterpret_cast<const char*>(l3) - ((uint64_t)kChildFlag << leaf_shift);

@@ -335,11 +335,9 @@ static cudaError_t run_pass(sdf::LevelPass<V> L, cudaStream_t stream, uint32_t* 
   constexpr size_t SLOTS = (size_t)1 << (3 * LOG2D);
   const size_t smem = (size_t)H * H * H * sizeof(V);
   const int threads = std::max(DIM * DIM, 32);
-  static bool attr_done = false;
-  if (!attr_done && smem > 48 * 1024) {
+  if (smem > 48 * 1024) {  // per device (and cheap): set on every call, so that a context on another GPU gets the opt-in too
     cudaError_t e = cudaFuncSetAttribute(sdf::sweep_kernel<LOG2D, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    attr_done = true;
   }
   if (L.n == 0) return cudaSuccess;
   const size_t cells = (size_t)L.n * SLOTS;
