@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define WX_ABI_VERSION 1
+#define WX_ABI_VERSION 2
 
 typedef enum WxStatus {
   WX_OK = 0,
@@ -203,6 +203,25 @@ int wx_render_device(WxContext *ctx, int device_index, const WxTree *tree, const
                      void *stream);
 
 int wx_last_render_info(const WxContext *ctx, WxRenderInfo *info);
+
+/*
+ * Per-context options (ABI 2).  They replace the getenv() knobs round 1 read inside the library: a release build reads no
+ * environment variable.  None of them changes a result except WX_OPT_MARCH.
+ */
+typedef enum WxOption {
+  WX_OPT_MARCH = 1,         /* 0 (default): exact -- frames and AOVs bit-identical to the strict-f32 restatement of the shader.
+                               1: tolerance mode -- the north-star bar (hit voxel + leaf equal on >= 99.9 % of the pixels, depth
+                               within 1e-4 relative, RGB within 1/255) instead of bit identity: p += t * dir may be one fused
+                               multiply-add and rays start at their entry into the active bounding box.  Render mode 2 (Ray:
+                               colours the iteration count) always takes the exact march. */
+  WX_OPT_KERNEL = 2,        /* 0 (default): tiled grid; 1: persistent kernel, warp-level tile queue; 2: persistent kernel,
+                               CTA-level chunk queue.  Same results; measured slower (profiles/). */
+  WX_OPT_RENDER_CHUNKS = 3, /* row chunks of a pipelined wx_render (0 = automatic) */
+  WX_OPT_SMEM_PAD = 4,      /* bytes of unused dynamic shared memory per CTA (lowers the resident CTAs per SM; measurement only) */
+  WX_OPT_NVTX = 5           /* 1: NVTX ranges around upload / sweep / render / read-back (default 0) */
+} WxOption;
+int wx_set_option(WxContext *ctx, int option, int64_t value);
+int wx_get_option(const WxContext *ctx, int option, int64_t *value_out);
 
 /*
  * Capture step after the raycast (replaces the copy_texture_to_buffer + recorder conversion of

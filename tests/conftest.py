@@ -23,6 +23,7 @@ def _built():
 @pytest.fixture(scope="session")
 def gpu_ctx():
     import woxel_b200 as W
-    ctx = W.Context()  # raises WxError(WX_ERR_NO_DEVICE) without a GPU: there is no CPU fallback
+    import knobs
+    ctx = knobs.apply_env(W.Context())  # raises WxError(WX_ERR_NO_DEVICE) without a GPU: there is no CPU fallback
     yield ctx
     ctx.close()

@@ -22,7 +22,7 @@ def test_cuda_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/woxel_b200.h but not exported"
     assert sorted(_ffi.CUDA_API) == names, "ctypes table and header are out of sync"
-    assert _ffi.cuda_lib().wx_abi_version() == 1
+    assert _ffi.cuda_lib().wx_abi_version() == 2
 
 
 def test_host_library_exports_every_declared_symbol():

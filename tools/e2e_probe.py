@@ -7,7 +7,7 @@ import bench
 import woxel_b200 as W
 from woxel_b200 import _ffi
 v, flat, what, prep = bench.build_scene("sphere2048")
-ctx = W.Context(); tree = ctx.upload(flat); st = bench.make_state("sphere2048", 0)
+import knobs; ctx = knobs.apply_env(W.Context()); tree = ctx.upload(flat); st = bench.make_state("sphere2048", 0)
 lib = _ffi.cuda_lib()
 nb = bench.WIDTH * bench.HEIGHT * 4
 pinned = C.c_void_p(); ctx.check(lib.wx_host_alloc_pinned(nb, C.byref(pinned)))

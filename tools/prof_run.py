@@ -20,7 +20,8 @@ ap.add_argument("--frames", type=int, default=4)
 ap.add_argument("--mode", type=int, default=0)
 a = ap.parse_args()
 v, flat, what, prep = bench.build_scene(a.scene)
-ctx = W.Context()
+import knobs  # noqa: E402
+ctx = knobs.apply_env(W.Context())
 tree = ctx.upload(flat)
 st = bench.make_state(a.scene, 0)
 st.render_mode[0] = a.mode

@@ -101,7 +101,11 @@ CUDA_API = {
     "wx_compute_sdf": (C.c_int, [vp, C.POINTER(WxTreeDesc), vp, vp, vp, C.c_uint32, C.POINTER(WxSdfInfo)]),
     "wx_capture_srgb": (C.c_int, [vp, C.c_uint32, C.c_uint32, C.c_uint32, vp]),
     "wx_srgb_table": (C.c_int, [vp]),
+    "wx_set_option": (C.c_int, [vp, C.c_int, C.c_int64]),
+    "wx_get_option": (C.c_int, [vp, C.c_int, C.POINTER(C.c_int64)]),
 }
+# WxOption (include/woxel_b200.h)
+WX_OPT_MARCH, WX_OPT_KERNEL, WX_OPT_RENDER_CHUNKS, WX_OPT_SMEM_PAD, WX_OPT_NVTX = 1, 2, 3, 4, 5
 f3, u3, i3 = C.POINTER(C.c_float), C.POINTER(C.c_uint32), C.POINTER(C.c_int32)
 HOST_API = {
     "wxh_last_error": (C.c_char_p, []),

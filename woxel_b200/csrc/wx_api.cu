@@ -66,6 +66,9 @@ struct WxContext {
   bool total_pending = false;
   WxRenderInfo info{};
   std::string last_error;
+  LaunchOptions opt;           // wx_set_option
+  uint32_t render_chunks = 0;  // WX_OPT_RENDER_CHUNKS (0 = automatic)
+  bool nvtx = false;           // WX_OPT_NVTX
 };
 
 struct TreeOnDevice {
@@ -576,7 +579,7 @@ static int launch_on(WxContext* ctx, int dev_i, const WxTree* tree, const WxStat
     P.row_base = row0, P.row_end = row1;
     uint32_t l = 0;
     uint32_t* counter = s.counters + (s.counter_next++ % kCounterRing);
-    const cudaError_t le = launch_raycast(P, e - b, mode, stream, &l, counter, s.resident_ctas);
+    const cudaError_t le = launch_raycast(P, e - b, mode, stream, &l, counter, s.resident_ctas, ctx->opt);
     if (le != cudaSuccess) {
       if (launch_states) (void)cudaFreeAsync(launch_states, stream);
       return fail_cuda(ctx, le, "launch_raycast");
@@ -679,8 +682,7 @@ static int render_distributed(WxContext* ctx, const WxTree* tree, const WxState*
     const uint32_t k = std::min<uint32_t>(n_states, 16u), per = (n_states + k - 1) / k;
     for (uint32_t c = 0; c < n_states; c += per) chunks.push_back(Chunk{c, std::min(n_states, c + per), 0, height});
   } else {
-    static const uint32_t k_env = getenv("WX_RENDER_CHUNKS") ? (uint32_t)atoi(getenv("WX_RENDER_CHUNKS")) : 0u;  // experiment knob
-    const uint32_t k = k_env ? k_env : ((uint64_t)width * height >= (1u << 20) ? std::max(2u, 8u / (uint32_t)ndev) : 1u);
+    const uint32_t k = ctx->render_chunks ? ctx->render_chunks : ((uint64_t)width * height >= (1u << 20) ? std::max(2u, 8u / (uint32_t)ndev) : 1u);
     const uint32_t round = (uint32_t)ndev * kBandRowsMultiple, rows = ((height + k - 1) / k + round - 1) / round * round;
     for (uint32_t r = 0; r < height; r += rows) chunks.push_back(Chunk{0, 1, r, std::min(height, r + rows)});
   }
@@ -816,8 +818,7 @@ extern "C" int wx_render(WxContext* ctx, const WxTree* tree, const WxState* stat
     std::vector<Chunk> chunks;
     if (!any_aov) {
       if (n_states == 1) {
-        static const uint32_t k_env = getenv("WX_RENDER_CHUNKS") ? (uint32_t)atoi(getenv("WX_RENDER_CHUNKS")) : 0u;  // experiment knob
-        const uint32_t k = k_env ? k_env : ((uint64_t)width * height >= (1u << 20) ? 8u : 1u);
+        const uint32_t k = ctx->render_chunks ? ctx->render_chunks : ((uint64_t)width * height >= (1u << 20) ? 8u : 1u);
         const uint32_t rows = ((height + k - 1) / k + kBandRowsMultiple - 1) / kBandRowsMultiple * kBandRowsMultiple;
         for (uint32_t r = 0; r < height; r += rows) chunks.push_back(Chunk{0, 1, r, std::min(height, r + rows)});
       } else {
@@ -935,6 +936,47 @@ extern "C" int wx_render(WxContext* ctx, const WxTree* tree, const WxState* stat
   ctx->info.launches = launches;
   ctx->info.rays = (uint64_t)(width / 8 * 8) * (height / 4 * 4) * n_states;
   return WX_OK;
+}
+
+extern "C" int wx_set_option(WxContext* ctx, int option, int64_t value) {
+  if (!ctx) return fail(nullptr, WX_ERR_INVALID_ARGUMENT, "wx_set_option: null context");
+  switch (option) {
+    case WX_OPT_MARCH:
+      if (value != 0 && value != 1) break;
+      ctx->opt.march = (int)value;
+      return WX_OK;
+    case WX_OPT_KERNEL:
+      if (value < 0 || value > 2) break;
+      ctx->opt.kernel = (int)value;
+      return WX_OK;
+    case WX_OPT_RENDER_CHUNKS:
+      if (value < 0 || value > 4096) break;
+      ctx->render_chunks = (uint32_t)value;
+      return WX_OK;
+    case WX_OPT_SMEM_PAD:
+      if (value < 0 || value > 200 * 1024) break;
+      ctx->opt.smem_pad = (size_t)value;
+      return WX_OK;
+    case WX_OPT_NVTX:
+      if (value != 0 && value != 1) break;
+      ctx->nvtx = value != 0;
+      return WX_OK;
+    default:
+      return fail(ctx, WX_ERR_INVALID_ARGUMENT, "wx_set_option: unknown option");
+  }
+  return fail(ctx, WX_ERR_INVALID_ARGUMENT, "wx_set_option: value out of range");
+}
+
+extern "C" int wx_get_option(const WxContext* ctx, int option, int64_t* value_out) {
+  if (!ctx || !value_out) return WX_ERR_INVALID_ARGUMENT;
+  switch (option) {
+    case WX_OPT_MARCH: *value_out = ctx->opt.march; return WX_OK;
+    case WX_OPT_KERNEL: *value_out = ctx->opt.kernel; return WX_OK;
+    case WX_OPT_RENDER_CHUNKS: *value_out = ctx->render_chunks; return WX_OK;
+    case WX_OPT_SMEM_PAD: *value_out = (int64_t)ctx->opt.smem_pad; return WX_OK;
+    case WX_OPT_NVTX: *value_out = ctx->nvtx ? 1 : 0; return WX_OK;
+    default: return WX_ERR_INVALID_ARGUMENT;
+  }
 }
 
 extern "C" int wx_shard_rows(uint32_t height, const WxShard* shard, uint8_t* row_mask_out) {

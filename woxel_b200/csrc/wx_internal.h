@@ -13,8 +13,14 @@ inline uint32_t shard_own_bands(uint32_t height, uint32_t index, uint32_t count,
 }
 // work_counter: one zero-initialisable u32 of device memory private to this launch (nullptr = tiled kernel);
 // resident_ctas: CTAs the device holds at once (SM count x CTAs per SM), the persistent grid.
+// Per-context options of wx_set_option (include/woxel_b200.h) that reach the launcher.
+struct LaunchOptions {
+  int kernel = 0;        // WX_OPT_KERNEL: 0 tiled grid, 1 warp-level tile queue, 2 CTA-level chunk queue
+  size_t smem_pad = 0;   // WX_OPT_SMEM_PAD
+  int march = 0;         // WX_OPT_MARCH: 0 exact, 1 tolerance mode
+};
 cudaError_t launch_raycast(RenderParams& P, uint32_t n_cams, uint32_t render_mode, cudaStream_t stream, uint32_t* launches,
-                           uint32_t* work_counter, uint32_t resident_ctas);
+                           uint32_t* work_counter, uint32_t resident_ctas, const LaunchOptions& opt);
 constexpr uint32_t kCtasPerSm = 9;
 // RGBA8 (linear) -> RGB8 through recorder.rs' linear_to_srgb; rgba_dev must be 16-byte aligned, rgb_dev 4-byte aligned.
 cudaError_t launch_srgb_rgb8(const uint8_t* rgba_dev, uint8_t* rgb_dev, size_t n_pixels, cudaStream_t stream);

@@ -3,8 +3,6 @@
 // is 8x4; the taller shape measured faster, see WX_WARP_W), a CTA is four such tiles side by side (16x8
 // pixels).  The per-pixel code (render_pixel, shade_and_store) lives in wx_device.cuh.
 #include <algorithm>
-#include <cstdlib>
-#include <string>
 
 #include "wx_device.cuh"
 #include "wx_internal.h"
@@ -135,16 +133,10 @@ static cudaError_t launch_mode_persistent(const RenderParams& P, unsigned ctas, 
   return cudaGetLastError();
 }
 
-// WX_SMEM_PAD: bytes of (unused) dynamic shared memory per CTA -- an experiment knob that lowers the number of resident
-// CTAs per SM to measure how the kernel responds to occupancy.
-static size_t smem_pad() {
-  static const size_t pad = getenv("WX_SMEM_PAD") ? (size_t)atoi(getenv("WX_SMEM_PAD")) : 0;
-  return pad;
-}
-
+// pad: bytes of (unused) dynamic shared memory per CTA (WX_OPT_SMEM_PAD) -- a measurement knob that lowers the number of
+// resident CTAs per SM.
 template <int MODE>
-static cudaError_t launch_mode(const RenderParams& P, dim3 grid, cudaStream_t stream) {
-  const size_t pad = smem_pad();
+static cudaError_t launch_mode(const RenderParams& P, dim3 grid, cudaStream_t stream, size_t pad) {
   if (pad > 48 * 1024) {
     (void)cudaFuncSetAttribute(raycast_kernel<MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pad);
     (void)cudaFuncSetAttribute(raycast_kernel<MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pad);
@@ -154,21 +146,15 @@ static cudaError_t launch_mode(const RenderParams& P, dim3 grid, cudaStream_t st
   return cudaGetLastError();
 }
 
-// WX_KERNEL=persistent selects the work-queue kernel.  Measured on the 4K sphere frame (profiles/r1_variants_e.txt):
-// tiled 0.995 ms, persistent 1.006 ms -- the CTA tail the queue removes is not what limits the tiled grid, so the
-// simpler kernel is the default.
-static int persistent_kind() {  // 0 tiled grid (default), 1 warp-level tile queue, 2 CTA-level chunk queue (experimental)
-  static const int kind = !getenv("WX_KERNEL") ? 0 : std::string(getenv("WX_KERNEL")) == "persistent" ? 1
-                          : std::string(getenv("WX_KERNEL")) == "persistent_cta" ? 2 : 0;
-  return kind;
-}
-static bool use_persistent() { return persistent_kind() != 0; }
+// WX_OPT_KERNEL selects a work-queue kernel.  Measured on the 4K sphere frame: tiled 0.924 ms, warp-level queue 0.964 ms,
+// CTA-level queue 1.985 ms (profiles/r2_cta_queue.txt) -- the CTA tail the queues remove is not what limits the tiled grid,
+// so the simpler kernel is the default.
 
 // Fills the launch geometry of P (shard -> bands -> tile rows) and launches frames
 // [P.cam_base, P.cam_base + n_cams) in render mode `render_mode` (the caller groups a camera batch
 // by mode).  P.n_states is the total number of states behind P.states / P.s0.
 cudaError_t launch_raycast(RenderParams& P, uint32_t n_cams, uint32_t render_mode, cudaStream_t stream, uint32_t* launches,
-                           uint32_t* work_counter, uint32_t resident_ctas) {
+                           uint32_t* work_counter, uint32_t resident_ctas, const LaunchOptions& opt) {
   *launches = 0;
   if (P.shard_count == 0) P.shard_count = 1, P.shard_index = 0;
   if (P.row_end == 0 || P.row_end > P.height) P.row_end = P.height;
@@ -192,7 +178,7 @@ cudaError_t launch_raycast(RenderParams& P, uint32_t n_cams, uint32_t render_mod
   if (P.own_bands == 0 || n_cams == 0 || P.tiles_x == 0) return cudaSuccess;
   const uint64_t tile_rows = (uint64_t)P.tile_rows_per_band * P.own_bands;
   if (P.tiles_x > 0x7fffffffu || tile_rows > 65535u || n_cams > 65535u) return cudaErrorInvalidConfiguration;
-  if (work_counter && use_persistent()) {
+  if (work_counter && opt.kernel != 0) {
     const uint64_t own_rows = (uint64_t)P.own_bands * P.band_rows;
     P.chunks_x = (P.width + 31u) / 32u;
     P.chunks_y = (uint32_t)((own_rows + 15u) / 16u);
@@ -205,7 +191,7 @@ cudaError_t launch_raycast(RenderParams& P, uint32_t n_cams, uint32_t render_mod
       // one warp per tile at most; otherwise every resident CTA slot of the device
       const unsigned ctas = (unsigned)std::min<uint64_t>((n_chunks * 16 + WX_CTA_WARPS - 1) / WX_CTA_WARPS, resident_ctas ? resident_ctas : 148u * (unsigned)(WX_MIN_BLOCKS));
       *launches = 1;
-      const bool cta_queue = persistent_kind() == 2;
+      const bool cta_queue = opt.kernel == 2;
       switch (render_mode) {
         case 1: return launch_mode_persistent<1>(P, ctas, stream, cta_queue);
         case 2: return launch_mode_persistent<2>(P, ctas, stream, cta_queue);
@@ -218,11 +204,11 @@ cudaError_t launch_raycast(RenderParams& P, uint32_t n_cams, uint32_t render_mod
   dim3 grid(P.tiles_x, (unsigned)tile_rows, n_cams);
   *launches = 1;
   switch (render_mode) {
-    case 1: return launch_mode<1>(P, grid, stream);
-    case 2: return launch_mode<2>(P, grid, stream);
-    case 3: return launch_mode<3>(P, grid, stream);
-    case 4: return launch_mode<4>(P, grid, stream);
-    default: return launch_mode<0>(P, grid, stream);  // Gray and the shader's `default:` arms
+    case 1: return launch_mode<1>(P, grid, stream, opt.smem_pad);
+    case 2: return launch_mode<2>(P, grid, stream, opt.smem_pad);
+    case 3: return launch_mode<3>(P, grid, stream, opt.smem_pad);
+    case 4: return launch_mode<4>(P, grid, stream, opt.smem_pad);
+    default: return launch_mode<0>(P, grid, stream, opt.smem_pad);  // Gray and the shader's `default:` arms
   }
 }
 

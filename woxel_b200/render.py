@@ -96,6 +96,15 @@ class Context:
     def device_count(self) -> int:
         return int(_ffi.cuda_lib().wx_device_count(self._h))
 
+    def set_option(self, option: int, value: int) -> None:
+        """wx_set_option (WX_OPT_* of include/woxel_b200.h / woxel_b200._ffi)."""
+        self.check(_ffi.cuda_lib().wx_set_option(self._h, int(option), int(value)))
+
+    def get_option(self, option: int) -> int:
+        v = C.c_int64(0)
+        self.check(_ffi.cuda_lib().wx_get_option(self._h, int(option), C.byref(v)))
+        return int(v.value)
+
     def upload(self, flat_or_desc) -> "Tree":
         return Tree(self, flat_or_desc)
 
