@@ -19,8 +19,14 @@ thread_local WxEmuTrace* wx_emu_trace = nullptr;
 namespace {
 using namespace wx;
 
+int g_march = 0;  // wxe_set_march: 0 exact, 1 tolerance mode (WX_OPT_MARCH); like the launcher, mode 2 always runs exact
 template <int MODE>
 void pixel(const RenderParams& P, const PixelRef& q) {
+  if (g_march == kMarchTolerance && MODE != 2) {
+    if (P.has_aov) render_pixel<MODE, true, kMarchTolerance>(P, q);
+    else render_pixel<MODE, false, kMarchTolerance>(P, q);
+    return;
+  }
   if (P.has_aov) render_pixel<MODE, true>(P, q);
   else render_pixel<MODE, false>(P, q);
 }
@@ -42,6 +48,7 @@ enum {
 };
 
 extern "C" int wxe_n_stats(void) { return WXE_N_STATS; }
+extern "C" void wxe_set_march(int march) { g_march = march; }
 
 // Renders states[0..n_states) (each in its own render mode) exactly as wx_render would.  warp_w x (32 / warp_w) is the
 // pixel footprint of a warp for the lockstep statistics (stats may be null; they cover the primary rays of mode-0 style
@@ -69,9 +76,10 @@ struct EmuScene {
     memset(&P, 0, sizeof(P));
     const bool fast_ok = fast_march_ok(leaf_bits, max5, max4, max3v);
     const bool with_grid = world_grid_ok(fast_ok, d->n4, d->n3);
-    if (with_grid) build_grid_tables(d->n5, d->n4, origins, root_grid, e5.data(), e4.data(), grid, f4);
+    int32_t bbox[6] = {1 << 30, 1 << 30, 1 << 30, -1, -1, -1};
+    if (with_grid) build_grid_tables(d->n5, d->n4, origins, root_grid, e5.data(), e4.data(), grid, f4), grid_bbox_cells(grid, bbox);
     fill_dev_tree(P.tree, e5.data(), e4.data(), l3.data(), origins.data(), d->n5, d->n4, d->n3, leaf_bits == 8 ? 9 : 11, fast_ok, root_grid,
-                  with_grid ? grid.data() : nullptr, with_grid ? f4.data() : nullptr);
+                  with_grid ? grid.data() : nullptr, with_grid ? f4.data() : nullptr, bbox);
     P.n_states = n_states;
     P.states = states;
     P.s0 = states[0];

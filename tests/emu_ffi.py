@@ -35,6 +35,8 @@ def lib() -> C.CDLL:
     L.wxe_chunk_coverage.restype = C.c_int
     L.wxe_chunk_coverage.argtypes = [C.c_uint32] * 6 + [C.c_void_p]
     L.wxe_n_stats.restype = C.c_int
+    L.wxe_set_march.restype = None
+    L.wxe_set_march.argtypes = [C.c_int]
     assert L.wxe_n_stats() == len(STAT_NAMES)
     return L
 
@@ -43,7 +45,8 @@ class Aov(C.Structure):  # == WxAov (include/woxel_b200.h)
     _fields_ = [(k, C.c_void_p) for k in ("state", "voxel", "leaf", "level", "iters", "depth", "mask", "pos")]
 
 
-def render(desc, states, width: int, height: int, aov: bool = True, rcp_bump: int = 0, warp_w: int = 4, stats: bool = False):
+def render(desc, states, width: int, height: int, aov: bool = True, rcp_bump: int = 0, warp_w: int = 4, stats: bool = False,
+           march: int = 0):
     """desc: WxTreeDesc (woxel_b200.render.make_desc); states: one or a list of 256-byte ComputeState objects.
     Returns (rgba[n,H,W,4], aov dict of [n,...] arrays or None, stats dict or None)."""
     if not isinstance(states, (list, tuple)):
@@ -65,8 +68,12 @@ def render(desc, states, width: int, height: int, aov: bool = True, rcp_bump: in
         }
         a = Aov(*[out[k].ctypes.data for k in ("state", "voxel", "leaf", "level", "iters", "depth", "mask", "pos")])
     st = np.zeros(len(STAT_NAMES), np.uint64) if stats else None
-    rc = lib().wxe_render(C.addressof(desc), C.addressof(buf), n, width, height, rgba.ctypes.data, C.addressof(a) if a is not None else None,
-                          rcp_bump, warp_w, st.ctypes.data if st is not None else None)
+    lib().wxe_set_march(march)  # 1: the tolerance-mode march (WX_OPT_MARCH); a process-wide switch of the emulation library
+    try:
+        rc = lib().wxe_render(C.addressof(desc), C.addressof(buf), n, width, height, rgba.ctypes.data, C.addressof(a) if a is not None else None,
+                              rcp_bump, warp_w, st.ctypes.data if st is not None else None)
+    finally:
+        lib().wxe_set_march(0)
     if rc != 0:
         raise RuntimeError(f"wxe_render failed: {rc}")
     return rgba, out, (dict(zip(STAT_NAMES, (int(v) for v in st))) if st is not None else None)

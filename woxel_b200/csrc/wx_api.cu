@@ -86,6 +86,7 @@ struct WxTree {
   uint32_t leaf_shift = 9;    // log2(bytes per leaf brick)
   bool fast_ok = true;        // every step size < 2^20: the fast march applies
   bool grid_ok = true;        // ... and the index bases of the world grid fit 32 bits: march_grid applies
+  int32_t bbox_cells[6] = {1 << 30, 1 << 30, 1 << 30, -1, -1, -1};  // grid_bbox_cells (tolerance-mode march)
   WxTreeInfo info{};
 };
 
@@ -131,6 +132,16 @@ __global__ void build_grid_kernel(const uint32_t* __restrict__ e5, const __grid_
   if (c >= kGS * kGS2) return;
   grid[(size_t)kGridPad + c] = grid_cell_entry(c >> 14, (c >> 7) & 127u, c & 127u, rg.v, e5);
 }
+// bbox[0..2] = min, bbox[3..5] = max cell coordinate of the in-world cells that are children or active tiles (grid_bbox_cells)
+__global__ void grid_bbox_kernel(const uint32_t* __restrict__ grid, int32_t* __restrict__ bbox) {
+  const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= 64u * 64u * 64u) return;
+  const uint32_t cx = 32u + (c >> 12), cy = 32u + ((c >> 6) & 63u), cz = 32u + (c & 63u);
+  const uint32_t e = grid[(size_t)kGridPad + (size_t)cx * kGS2 + (size_t)cy * kGS + cz];
+  if (!((e & kChildFlag) || e == 0u)) return;
+  atomicMin(bbox + 0, (int32_t)cx), atomicMin(bbox + 1, (int32_t)cy), atomicMin(bbox + 2, (int32_t)cz);
+  atomicMax(bbox + 3, (int32_t)cx), atomicMax(bbox + 4, (int32_t)cy), atomicMax(bbox + 5, (int32_t)cz);
+}
 __global__ void build_f4_kernel(const uint32_t* __restrict__ e4, const uint32_t* __restrict__ o4, uint32_t n4, uint32_t* __restrict__ f4) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (size_t)n4 * 4096u) return;
@@ -142,8 +153,11 @@ __global__ void build_f4_kernel(const uint32_t* __restrict__ e4, const uint32_t*
 }  // namespace
 
 // Current device = the replica's device; everything is enqueued on `stream` (the scratch is freed in stream order).
+// bbox_host (optional, 6 ints): receives grid_bbox_cells of the new grid (the copy is stream-ordered into pageable memory, i.e.
+// complete when this returns).
 static cudaError_t build_grid_on_device(uint32_t*& grid, uint32_t*& f4, const uint32_t* e5, const uint32_t* e4, const int4* origins,
-                                        uint32_t n5, uint32_t n4, const int16_t root_grid[64], cudaStream_t stream) {
+                                        uint32_t n5, uint32_t n4, const int16_t root_grid[64], cudaStream_t stream,
+                                        int32_t* bbox_host = nullptr) {
   cudaError_t e = cudaMalloc(&grid, kGridCells * 4);
   if (e == cudaSuccess) e = cudaMalloc(&f4, (size_t)n4 * 4096u * 4u + 256);
   uint32_t* o4 = nullptr;
@@ -163,6 +177,17 @@ static cudaError_t build_grid_on_device(uint32_t*& grid, uint32_t*& f4, const ui
   if (e == cudaSuccess && n4) {
     build_f4_kernel<<<(unsigned)(((size_t)n4 * 4096u + 255) / 256), 256, 0, stream>>>(e4, o4, n4, f4);
     e = cudaGetLastError();
+  }
+  if (e == cudaSuccess && bbox_host) {
+    int32_t* bb = reinterpret_cast<int32_t*>(o4);  // the scratch is free again once build_f4_kernel has run (stream order)
+    const int32_t init[6] = {1 << 30, 1 << 30, 1 << 30, -1, -1, -1};
+    e = cudaMemcpyAsync(bb, init, sizeof(init), cudaMemcpyHostToDevice, stream);
+    if (e == cudaSuccess) {
+      grid_bbox_kernel<<<64 * 64 * 64 / 256, 256, 0, stream>>>(grid, bb);
+      e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(bbox_host, bb, sizeof(init), cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
   }
   const cudaError_t fe = cudaFreeAsync(o4, stream);
   return e != cudaSuccess ? e : fe;
@@ -355,7 +380,7 @@ extern "C" int wx_tree_upload(WxContext* ctx, const WxTreeDesc* d, WxTree** out)
     if (!l3.empty()) WX_CUDA(ctx, cudaMemcpyAsync(o.l3, l3.data(), l3.size(), cudaMemcpyHostToDevice, s.stream));
     if (!t->origins.empty())
       WX_CUDA(ctx, cudaMemcpyAsync(o.origins, t->origins.data(), t->origins.size() * sizeof(int4), cudaMemcpyHostToDevice, s.stream));
-    if (t->grid_ok) WX_CUDA(ctx, build_grid_on_device(o.grid, o.f4, o.e5, o.e4, o.origins, d->n5, d->n4, t->root_grid, s.stream));
+    if (t->grid_ok) WX_CUDA(ctx, build_grid_on_device(o.grid, o.f4, o.e5, o.e4, o.origins, d->n5, d->n4, t->root_grid, s.stream, dev_i == 0 ? t->bbox_cells : nullptr));
     return WX_OK;
   };
   for (int i = 0; i < (int)ctx->dev.size(); ++i) {
@@ -467,7 +492,7 @@ extern "C" int wx_tree_build(WxContext* ctx, const WxTreeDesc* d, WxTree** out, 
     if (e != cudaSuccess) return bail(e, "wx_tree_build: origins");
   }
   if (t->grid_ok) {
-    e = build_grid_on_device(t->on[0].grid, t->on[0].f4, first.e5, first.e4, first.origins, d->n5, d->n4, t->root_grid, d0.stream);
+    e = build_grid_on_device(t->on[0].grid, t->on[0].f4, first.e5, first.e4, first.origins, d->n5, d->n4, t->root_grid, d0.stream, t->bbox_cells);
     if (e != cudaSuccess) return bail(e, "wx_tree_build: world grid");
   }
   // replicate read-only on the other devices of the context (peer copies over NVLink)
@@ -540,7 +565,7 @@ static int launch_on(WxContext* ctx, int dev_i, const WxTree* tree, const WxStat
   RenderParams P;
   memset(&P, 0, sizeof(P));
   fill_dev_tree(P.tree, o.e5, o.e4, o.l3, o.origins, tree->info.n5, tree->info.n4, tree->info.n3, tree->leaf_shift, tree->fast_ok,
-                tree->root_grid, o.grid, o.f4);
+                tree->root_grid, o.grid, o.f4, tree->bbox_cells);
   P.n_states = n_states;
   P.width = width, P.height = height;
   P.rgba = reinterpret_cast<uchar4*>(rgba_dev);

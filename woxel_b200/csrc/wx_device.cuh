@@ -71,6 +71,9 @@ struct DevTree {
   // World grid (the march's usual top level, see "World grid" below); grid == nullptr when the tree does not qualify.
   const uint32_t* __restrict__ grid;  // kGridCells entries
   const uint32_t* __restrict__ f4;    // re-encoded N4 tables: the child entries of e4 as index bases (grid_word3)
+  // Bounding box (voxel coordinates, 128-voxel cell granularity) of everything a ray can hit: the in-world grid cells that are
+  // children or active tiles.  Used only by the tolerance-mode march (WX_OPT_MARCH = 1); bb_lo[0] > bb_hi[0] = empty / unknown.
+  float bb_lo[3], bb_hi[3];
 #ifdef WX_ROOT_PTRS
   // A/B variant (measured 0.7 % SLOWER than the int16 cells + address arithmetic, profiles/r1_variants_h.txt; not the default):
   // the same cells as ready-made N5 table addresses of THIS replica: kRootPtrNone = no N5, kRootPtrScan = scan the
@@ -161,6 +164,8 @@ struct RenderParams {
   AovPtrs aov;
   uint32_t has_aov;
 };
+// MARCH template parameter of the kernels: how hdda_ray is evaluated (WX_OPT_MARCH)
+constexpr int kMarchExact = 0, kMarchTolerance = 1;
 
 // ---------------------------------------------------------------------------------------------
 // small vector helpers (plain IEEE ops; no contraction in this TU)
@@ -695,6 +700,9 @@ struct GridRay {
   // One iteration of hdda_ray's loop body (:90-122) without the counter: `last` is the voxel of the lookup before, `cur`
   // receives this one's (the caller alternates two VoxelIds, so nothing is copied).  Returns true when the ray left the
   // loop: a hit (size == 0) or a slow cell (0 < size < 1).
+  // TOL (tolerance mode, WX_OPT_MARCH = 1): p += t * dir is one fused multiply-add per axis -- one rounding instead of two,
+  // three instructions fewer; no longer bit-identical to the strict restatement, but within the north-star bar against it.
+  template <bool TOL>
   __device__ __forceinline__ bool step(const DevTree& T, const VoxelId& last, VoxelId& cur) {
     const f32x2 txy = add2_rd(pxy, bc(kMagic));
     const float tz = __fadd_rd(pz, kMagic);
@@ -733,9 +741,16 @@ struct GridRay {
     const float tmz = iz * fmaf(size, s01z, nmz);
     ltx = lo(tmxy), lty = hi(tmxy), ltz = tmz;
     lt = fminf(fminf(ltx, lty), ltz);
-    const f32x2 axy = mul2(bc(lt), dxy);
-    float px = lo(pxy) + lo(axy), py = hi(pxy) + hi(axy);
-    pz = pz + lt * dz;
+    float px, py;
+    if (TOL) {
+      const f32x2 nxy = fma2(bc(lt), dxy, pxy);
+      px = lo(nxy), py = hi(nxy);
+      pz = fmaf(lt, dz, pz);
+    } else {
+      const f32x2 axy = mul2(bc(lt), dxy);
+      px = lo(pxy) + lo(axy), py = hi(pxy) + hi(axy);
+      pz = pz + lt * dz;
+    }
     if (ltx == lt) px += ndx;
     if (lty == lt) py += ndy;
     if (ltz == lt) pz += ndz;
@@ -744,18 +759,35 @@ struct GridRay {
   }
 };
 
+// Tolerance mode only: a ray that starts outside the bounding box of everything it could hit and crosses it starts two voxels
+// before its entry point instead (the steps through the empty tiles in front of the box are skipped; the iteration count
+// changes, which is why render mode 2 never runs in this mode).  Rays that miss the box are left alone: the colour of an
+// out-of-bounds pixel depends on the axis of the ray's LAST step, which only the full march knows.
+__device__ __forceinline__ V3 clip_to_bbox(const DevTree& T, V3 src, V3 dir, V3 idir) {
+  if (T.bb_lo[0] > T.bb_hi[0] || out_of_bounds(src.x, src.y, src.z)) return src;  // (a start outside the world ends at once, :100-103)
+  const float ax = (T.bb_lo[0] - src.x) * idir.x, bx = (T.bb_hi[0] - src.x) * idir.x;
+  const float ay = (T.bb_lo[1] - src.y) * idir.y, by = (T.bb_hi[1] - src.y) * idir.y;
+  const float az = (T.bb_lo[2] - src.z) * idir.z, bz = (T.bb_hi[2] - src.z) * idir.z;
+  const float t_near = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz));
+  const float t_far = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
+  if (!(t_near < t_far) || !(t_near > 2.f)) return src;  // misses the box, or starts inside / right in front of it (NaNs: no clip)
+  const float t = t_near - 2.f;
+  return V3{fmaf(t, dir.x, src.x), fmaf(t, dir.y, src.y), fmaf(t, dir.z, src.z)};
+}
+
+template <bool TOL>
 __device__ __forceinline__ HitOut march_grid(const DevTree& T, V3 src, V3 dir, V3 idir) {
   GridRay r;
-  r.init(src, dir, idir);
+  r.init(TOL ? clip_to_bbox(T, src, dir, idir) : src, dir, idir);
   // Two steps per trip over two alternating VoxelIds: nothing is copied inside the loop, and the step budget (kMaxRaySteps
   // is even) is tested once per trip.  The copies at the exits are opaque so that the compiler does not merge a and b.
   VoxelId a{0u, 0u, 0u}, b{0u, 0u, 0u}, v;
   for (;;) {
-    if (r.step(T, a, b)) {
+    if (r.template step<TOL>(T, a, b)) {
       v = opaque_copy(b);
       break;
     }
-    if (r.step(T, b, a)) {
+    if (r.template step<TOL>(T, b, a)) {
       v = opaque_copy(a), r.i += 1u;
       break;
     }
@@ -800,17 +832,19 @@ __device__ __forceinline__ bool fast_ray_ok(const DevTree& T, V3 src, V3 idir) {
          fmaxf(fmaxf(fabsf(src.x), fabsf(src.y)), fabsf(src.z)) < 2097152.f;
 }
 
+template <int MARCH>
 __device__ __forceinline__ HitOut hdda_ray(const DevTree& T, V3 src, V3 dir) {
   const V3 idir = V3{1.f / dir.x, 1.f / dir.y, 1.f / dir.z};
 #ifndef WX_NO_GRID
-  if (grid_ray_ok(T, src, idir)) return march_grid(T, src, dir, idir);
+  if (grid_ray_ok(T, src, idir)) return march_grid<MARCH == kMarchTolerance>(T, src, dir, idir);
 #endif
   if (fast_ray_ok(T, src, idir)) return march_fast(T, src, dir, idir);
   return march_exact(T, src, dir);
 }
 
 // secondary rays share one out-of-line copy of the march
-static __device__ __noinline__ HitOut hdda_ray_secondary(const DevTree& T, V3 src, V3 dir) { return hdda_ray(T, src, dir); }
+template <int MARCH>
+static __device__ __noinline__ HitOut hdda_ray_secondary(const DevTree& T, V3 src, V3 dir) { return hdda_ray<MARCH>(T, src, dir); }
 
 // ---------------------------------------------------------------------------------------------
 // shading (raycast.comp.wgsl:144-342)
@@ -840,31 +874,34 @@ __device__ __forceinline__ V3 wall_flat(V3 N) {
 }
 
 // BASE + I * sun, with the sun term x0.05 when a shadow ray finds an occluder (:199-208, :280-290, :317-325)
+template <int MARCH>
 __device__ __forceinline__ V3 sun_lit(const DevTree& T, const WxState& s, const HitOut& hit, V3 step, V3 N) {
   float I = s.sun_color[3] * WX_K_D * dot3(-sun_dir(s), N);
   I = fmaxf(0.0f, I);
-  if (I != 0.0f && hdda_ray_secondary(T, hit.p - (4e-2f * step) * maskf(hit.mask), -sun_dir(s)).state == 0u)
+  if (I != 0.0f && hdda_ray_secondary<MARCH>(T, hit.p - (4e-2f * step) * maskf(hit.mask), -sun_dir(s)).state == 0u)
     return WX_BASE_COLOR + (I * sun_rgb(s)) * 0.05f;
   return WX_BASE_COLOR + I * sun_rgb(s);
 }
 
+template <int MARCH>
 __device__ __forceinline__ V3 reflect_ray1(const DevTree& T, const WxState& s, V3 src, V3 dir) {
-  const HitOut hit = hdda_ray_secondary(T, src, dir);
+  const HitOut hit = hdda_ray_secondary<MARCH>(T, src, dir);
   const V3 step = sign11(dir);
-  if (hit.state == 0u) return sun_lit(T, s, hit, step, normalize3((-step) * maskf(hit.mask)));
+  if (hit.state == 0u) return sun_lit<MARCH>(T, s, hit, step, normalize3((-step) * maskf(hit.mask)));
   if (hit.state == 1u) return wall_flat(normalize3((-step) * maskf(hit.mask)));
   return dir;
 }
 
+template <int MARCH>
 __device__ __forceinline__ V3 reflect_ray2(const DevTree& T, const WxState& s, V3 src, V3 dir) {
-  const HitOut hit = hdda_ray_secondary(T, src, dir);
+  const HitOut hit = hdda_ray_secondary<MARCH>(T, src, dir);
   const V3 step = sign11(dir);
   if (hit.state == 0u) {
     const V3 N = normalize3((-step) * maskf(hit.mask));
     const V3 rdir = normalize3(dir - (2.0f * N) * dot3(dir, N));
     const V3 rsrc = hit.p - (4e-2f * step) * maskf(hit.mask);
-    const V3 rcol = reflect_ray1(T, s, rsrc, rdir);
-    const V3 mcol = sun_lit(T, s, hit, step, N);
+    const V3 rcol = reflect_ray1<MARCH>(T, s, rsrc, rdir);
+    const V3 mcol = sun_lit<MARCH>(T, s, hit, step, N);
     return mix3(mcol, rcol, WX_REFLECTIVITY);
   }
   if (hit.state == 1u) return wall_flat(normalize3((-step) * maskf(hit.mask)));
@@ -877,7 +914,7 @@ __device__ __forceinline__ bool any_mod0(V3 fp, float m) {
 }
 
 // ray_trace (:152-265) given the primary HitOut.  MODE is the warp-uniform render mode.
-template <int MODE>
+template <int MODE, int MARCH>
 __device__ __forceinline__ V3 shade(const DevTree& T, const WxState& s, const HitOut& hit, V3 dir) {
   const V3 step = sign11(dir);
   if (hit.state == 0u) {
@@ -898,15 +935,15 @@ __device__ __forceinline__ V3 shade(const DevTree& T, const WxState& s, const Hi
       const float LN = fmaxf(0.0f, s.sun_color[3] * dot3(-sun_dir(s), N));
       const V3 I_d = ((WX_K_D * sun_rgb(s)) * WX_BASE_COLOR) * LN;
       const V3 I_a = (WX_K_A * WX_AMBIENT_COLOR) * WX_BASE_COLOR;
-      if (LN != 0.0f && hdda_ray_secondary(T, hit.p - (4e-2f * step) * maskf(hit.mask), -sun_dir(s)).state == 0u) return I_a;
+      if (LN != 0.0f && hdda_ray_secondary<MARCH>(T, hit.p - (4e-2f * step) * maskf(hit.mask), -sun_dir(s)).state == 0u) return I_a;
       return I_a + I_d;
     }
     if (MODE == 4) {
       const V3 N = normalize3((-step) * maskf(hit.mask));
-      const V3 mcol = sun_lit(T, s, hit, step, N);
+      const V3 mcol = sun_lit<MARCH>(T, s, hit, step, N);
       const V3 rdir = normalize3(dir - (2.0f * N) * dot3(dir, N));
       const V3 rsrc = hit.p - (4e-2f * step) * maskf(hit.mask);
-      const V3 rcol = reflect_ray2(T, s, rsrc, rdir);
+      const V3 rcol = reflect_ray2<MARCH>(T, s, rsrc, rdir);
       return mix3(mcol, rcol, WX_REFLECTIVITY);
     }
     return grid + dot3(maskf(hit.mask) * V3{0.2f, 0.2f, 0.3f}, splat(1.0f));  // Gray and any other mode
@@ -951,11 +988,11 @@ struct PixelRef {
   bool dispatched;  // inside the reference's dispatch (wgpu_context.rs:281)
 };
 
-template <int MODE, bool AOV>
+template <int MODE, bool AOV, int MARCH>
 __device__ __forceinline__ void shade_and_store(const RenderParams& P, const PixelRef& q, const HitOut& hit, V3 dir) {
   const WxState& s = (P.n_states == 1) ? P.s0 : P.states[q.cam];
   const size_t pix = ((size_t)q.cam * P.height + q.y) * P.width + q.x;
-  const V3 col = shade<MODE>(P.tree, s, hit, dir);
+  const V3 col = shade<MODE, MARCH>(P.tree, s, hit, dir);
   P.rgba[pix] = make_uchar4((unsigned char)unorm8(col.x), (unsigned char)unorm8(col.y), (unsigned char)unorm8(col.z), 255);
   if (AOV) {
     const AovPtrs& a = P.aov;
@@ -978,7 +1015,7 @@ __device__ __forceinline__ void shade_and_store(const RenderParams& P, const Pix
 }
 
 // cp_main (:60-68) for one pixel: ray generation, hdda_ray, ray_trace, store.
-template <int MODE, bool AOV>
+template <int MODE, bool AOV, int MARCH = kMarchExact>
 __device__ __forceinline__ void render_pixel(const RenderParams& P, const PixelRef& q) {
   if (!q.in_frame) return;
   if (!q.dispatched) {  // never dispatched by the reference: zero-initialised texel (and zeroed AOVs)
@@ -1009,7 +1046,7 @@ __device__ __forceinline__ void render_pixel(const RenderParams& P, const PixelR
   }
   const float px = (float)q.x + 0.001f, py = (float)q.y + 0.001f;
   const V3 dir = normalize3((px * u + py * mv) + wp);
-  shade_and_store<MODE, AOV>(P, q, hdda_ray(P.tree, eye, dir), dir);
+  shade_and_store<MODE, AOV, MARCH>(P, q, hdda_ray<MARCH>(P.tree, eye, dir), dir);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -176,12 +176,30 @@ static inline void build_grid_tables(uint32_t n5, uint32_t n4, const std::vector
   });
 }
 
+// Bounding box of what a ray can hit, in grid cells (lo xyz, hi xyz inclusive; lo > hi = empty): the in-world cells that are
+// children or active tiles (host version; wx_api.cu reduces the same on the device).
+static inline void grid_bbox_cells(const std::vector<uint32_t>& grid, int32_t bbox[6]) {
+  bbox[0] = bbox[1] = bbox[2] = 1 << 30, bbox[3] = bbox[4] = bbox[5] = -1;
+  for (uint32_t cx = 32; cx < 96; ++cx)
+    for (uint32_t cy = 32; cy < 96; ++cy)
+      for (uint32_t cz = 32; cz < 96; ++cz) {
+        const uint32_t e = grid[(size_t)kGridPad + (size_t)cx * kGS2 + (size_t)cy * kGS + cz];
+        if (!((e & kChildFlag) || e == 0u)) continue;
+        const int32_t c[3] = {(int32_t)cx, (int32_t)cy, (int32_t)cz};
+        for (int k = 0; k < 3; ++k) bbox[k] = std::min(bbox[k], c[k]), bbox[3 + k] = std::max(bbox[3 + k], c[k]);
+      }
+}
+
 // The kernel's view of one replica of the tree.  grid / f4: nullptr when the tree has no world grid.
 static inline void fill_dev_tree(DevTree& T, const uint32_t* e5, const uint32_t* e4, const uint8_t* l3, const int4* origins, uint32_t n5,
                                  uint32_t n4, uint32_t n3, uint32_t leaf_shift, bool fast_ok, const int16_t root_grid[64],
-                                 const uint32_t* grid = nullptr, const uint32_t* f4 = nullptr) {
+                                 const uint32_t* grid = nullptr, const uint32_t* f4 = nullptr, const int32_t* bbox_cells = nullptr) {
   T.e5 = e5, T.e4 = e4, T.l3 = l3, T.origins_g = origins;
   T.grid = (grid && f4) ? grid : nullptr, T.f4 = f4;
+  T.bb_lo[0] = 1.f, T.bb_hi[0] = 0.f;  // empty
+  if (bbox_cells && bbox_cells[0] <= bbox_cells[3]) {  // grid cells (lo xyz, hi xyz inclusive) -> voxel coordinates
+    for (int k = 0; k < 3; ++k) T.bb_lo[k] = (float)((bbox_cells[k] - 64) * 128), T.bb_hi[k] = (float)((bbox_cells[3 + k] - 64 + 1) * 128);
+  }
   // a child entry keeps its flag bit: node = adj + entry * node_bytes, adj = base - 2^31 * node_bytes
   T.e4_adj = reinterpret_cast<const char*>(e4) - ((uint64_t)kChildFlag << 14);
   T.l3_adj = reinterpret_cast<const char*>(l3) - ((uint64_t)kChildFlag << leaf_shift);

@@ -49,6 +49,24 @@ __global__ void __launch_bounds__(kThreads, WX_MIN_BLOCKS) raycast_kernel(const 
   render_pixel<MODE, AOV>(P, q);
 }
 
+// The same kernel in tolerance mode (WX_OPT_MARCH = 1, wx_device.cuh: fused p += t * dir, rays start at the bounding box of
+// the active cells).  A separate entry point so that the exact kernel's symbol, registers and SASS do not depend on it.
+template <int MODE, bool AOV>
+__global__ void __launch_bounds__(kThreads, WX_MIN_BLOCKS) raycast_kernel_tol(const __grid_constant__ RenderParams P) {
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint32_t own_band = 0, in_band = blockIdx.y;
+  if (P.tile_rows_per_band == 1u) own_band = blockIdx.y, in_band = 0;
+  else if (P.own_bands > 1u) own_band = blockIdx.y / P.tile_rows_per_band, in_band = blockIdx.y - own_band * P.tile_rows_per_band;
+  const uint32_t band = own_band * P.shard_count + P.shard_index;
+  PixelRef q;
+  q.x = blockIdx.x * kTileW + WX_LANE_X(warp, lane);
+  q.y = P.row_base + band * P.band_rows + in_band * kTileH + WX_LANE_Y(warp, lane);
+  q.cam = P.cam_base + blockIdx.z;
+  q.in_frame = q.x < P.width && q.y < P.row_end;
+  q.dispatched = q.x < P.disp_w && q.y < P.disp_h;
+  render_pixel<MODE, AOV, kMarchTolerance>(P, q);
+}
+
 // ---------------------------------------------------------------------------------------------
 // Persistent kernel: the grid is the number of CTAs the device holds at once; every warp pulls 8x4-pixel
 // tiles from a global counter until the frame is done.  Tiles are numbered so that 16 consecutive ones
@@ -145,6 +163,12 @@ static cudaError_t launch_mode(const RenderParams& P, dim3 grid, cudaStream_t st
   else raycast_kernel<MODE, false><<<grid, kThreads, pad, stream>>>(P);
   return cudaGetLastError();
 }
+template <int MODE>
+static cudaError_t launch_mode_tol(const RenderParams& P, dim3 grid, cudaStream_t stream) {
+  if (P.has_aov) raycast_kernel_tol<MODE, true><<<grid, kThreads, 0, stream>>>(P);
+  else raycast_kernel_tol<MODE, false><<<grid, kThreads, 0, stream>>>(P);
+  return cudaGetLastError();
+}
 
 // WX_OPT_KERNEL selects a work-queue kernel.  Measured on the 4K sphere frame: tiled 0.924 ms, warp-level queue 0.964 ms,
 // CTA-level queue 1.985 ms (profiles/r2_cta_queue.txt) -- the CTA tail the queues remove is not what limits the tiled grid,
@@ -178,7 +202,7 @@ cudaError_t launch_raycast(RenderParams& P, uint32_t n_cams, uint32_t render_mod
   if (P.own_bands == 0 || n_cams == 0 || P.tiles_x == 0) return cudaSuccess;
   const uint64_t tile_rows = (uint64_t)P.tile_rows_per_band * P.own_bands;
   if (P.tiles_x > 0x7fffffffu || tile_rows > 65535u || n_cams > 65535u) return cudaErrorInvalidConfiguration;
-  if (work_counter && opt.kernel != 0) {
+  if (work_counter && opt.kernel != 0 && opt.march == kMarchExact) {
     const uint64_t own_rows = (uint64_t)P.own_bands * P.band_rows;
     P.chunks_x = (P.width + 31u) / 32u;
     P.chunks_y = (uint32_t)((own_rows + 15u) / 16u);
@@ -203,6 +227,14 @@ cudaError_t launch_raycast(RenderParams& P, uint32_t n_cams, uint32_t render_mod
   }
   dim3 grid(P.tiles_x, (unsigned)tile_rows, n_cams);
   *launches = 1;
+  if (opt.march == kMarchTolerance && render_mode != 2u) {  // mode 2 colours the iteration count: always exact
+    switch (render_mode) {
+      case 1: return launch_mode_tol<1>(P, grid, stream);
+      case 3: return launch_mode_tol<3>(P, grid, stream);
+      case 4: return launch_mode_tol<4>(P, grid, stream);
+      default: return launch_mode_tol<0>(P, grid, stream);
+    }
+  }
   switch (render_mode) {
     case 1: return launch_mode<1>(P, grid, stream, opt.smem_pad);
     case 2: return launch_mode<2>(P, grid, stream, opt.smem_pad);
