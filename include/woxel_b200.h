@@ -202,6 +202,16 @@ int wx_render_device(WxContext *ctx, int device_index, const WxTree *tree, const
                      uint32_t width, uint32_t height, uint8_t *rgba_dev, const WxAov *aov_dev, const WxShard *shard,
                      void *stream);
 
+/*
+ * One shard of a frame that is split over several processes, one per GPU (BASELINE config 4's tile partition; wx_render on a
+ * multi-device context does the same inside one process).  Renders the rows `shard` selects (bands of 8 rows, band b belongs to
+ * shard b % count) of every frame into the context's own memory and delivers exactly those rows to rgba_out, which has the
+ * layout of the whole frame stack: host memory, or device memory of any GPU -- e.g. a frame on GPU 0 opened with
+ * wx_ipc_open, the rows then travel over NVLink by DMA.  Blocking.  shard->band_rows must be 8.
+ */
+int wx_render_shard(WxContext *ctx, const WxTree *tree, const WxState *states, uint32_t n_states, uint32_t width,
+                    uint32_t height, const WxShard *shard, uint8_t *rgba_out);
+
 int wx_last_render_info(const WxContext *ctx, WxRenderInfo *info);
 
 /*

@@ -172,6 +172,16 @@ extern "C" {
         shard: *const WxShard,
         stream: *mut c_void,
     ) -> c_int;
+    pub fn wx_render_shard(
+        ctx: *mut WxContext,
+        tree: *const WxTree,
+        states: *const WxState,
+        n_states: u32,
+        width: u32,
+        height: u32,
+        shard: *const WxShard,
+        rgba_out: *mut u8,
+    ) -> c_int;
     pub fn wx_last_render_info(ctx: *const WxContext, info: *mut WxRenderInfo) -> c_int;
 
     pub fn wx_set_option(ctx: *mut WxContext, option: c_int, value: i64) -> c_int;

@@ -23,6 +23,24 @@ def test_reference_arm_prints_one_contract_line():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"] and "model" not in d["config"]
+    assert d["warmup"] == 3  # W >= 3 as in the GPU arm, never capped: the driver's warmup_match
+    # the two arms print the same `config` (the driver's same_config)
+    import bench
+    assert d["config"] == bench.workload_config(d["config"]["workload"].split(", 3840x2160")[0])
+
+
+def test_traffic_json_carries_the_kernel_hash():
+    """profiles/traffic.json describes ONE build of the raycast kernel: it stores that kernel's SASS md5, bench.py compares it
+    with the loaded library's and says `traffic_stale` when they differ.  Here: the committed figures belong to the committed kernel."""
+    import json
+    import shutil
+    import pytest
+    import bench
+    prof = json.load(open(os.path.join(bench.ROOT, "profiles", "traffic.json")))["sphere2048"]
+    assert len(prof["sass_md5"]) == 32 and prof["warp_instructions_per_launch"] > 1e8
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("no cuobjdump")
+    assert bench.sass_md5_of_loaded_kernel() == prof["sass_md5"], "profiles/traffic.json is stale: re-capture (tools/update_traffic.py)"
 
 
 def test_other_ranks_of_the_reference_arm_exit_quietly():

@@ -177,3 +177,26 @@ def test_mutated_blosc_frames_never_crash(codec):
             except W.vdb.VdbError:
                 bad += 1
     assert ok + bad == 750 and bad > 100
+
+
+def test_crafted_blosc_header_is_rejected_before_any_allocation():
+    """A 16-byte frame whose header claims 4 GiB: the decoder must refuse from the header alone -- the size is
+    checked against what the caller expects / has room for, and against what the stored bytes could possibly expand to."""
+    import ctypes as C
+    import time
+    from woxel_b200 import _ffi
+    lib = _ffi.host_lib()
+    for flags in (0x21, 0x01, 0x61, 0x25):  # LZ4 / BloscLZ / zlib with byte shuffle, LZ4 with bit shuffle
+        frame = bytes([2, 1, flags, 4]) + (0xFFFFFFF0).to_bytes(4, "little") + (0xFFFFFFF0).to_bytes(4, "little") + (16).to_bytes(4, "little")
+        out = C.create_string_buffer(1 << 16)
+        n = C.c_size_t(0)
+        t0 = time.perf_counter()
+        rc = lib.wxh_blosc_decompress(frame, len(frame), out, len(out), C.byref(n))
+        assert rc != 0 and time.perf_counter() - t0 < 0.05, (flags, rc)
+        # the same header with room for it: still refused (16 stored bytes cannot expand to 4 GiB)
+        frame2 = frame + b"\0" * 64
+        frame2 = frame2[:12] + len(frame2).to_bytes(4, "little") + frame2[16:]
+        t0 = time.perf_counter()
+        with pytest.raises(W.vdb.VdbError):
+            W.vdb.blosc_decompress(frame2[:4] + (1 << 20).to_bytes(4, "little") + (0xFFFFFFF0).to_bytes(4, "little") + frame2[12:])
+        assert time.perf_counter() - t0 < 0.5

@@ -86,6 +86,7 @@ CUDA_API = {
     "wx_render": (C.c_int, [vp, vp, C.POINTER(WxState), C.c_uint32, C.c_uint32, C.c_uint32, vp, C.POINTER(WxAov)]),
     "wx_render_device": (C.c_int, [vp, C.c_int, vp, C.POINTER(WxState), C.c_uint32, C.c_uint32, C.c_uint32, vp,
                                    C.POINTER(WxAov), C.POINTER(WxShard), vp]),
+    "wx_render_shard": (C.c_int, [vp, vp, C.POINTER(WxState), C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(WxShard), vp]),
     "wx_last_render_info": (C.c_int, [vp, C.POINTER(WxRenderInfo)]),
     "wx_device_alloc": (C.c_int, [vp, C.c_int, C.c_size_t, C.POINTER(vp)]),
     "wx_device_free": (C.c_int, [vp, C.c_int, vp]),
@@ -163,6 +164,11 @@ def _load(path: str, api: dict) -> C.CDLL:
 
 _cuda = None
 _host = None
+
+
+def cuda_lib_path() -> str:
+    """Path of the CUDA library this process loads (WOXEL_B200_LIB selects a build-time variant for A/B runs)."""
+    return CUDA_LIB_PATH
 
 
 def cuda_lib() -> C.CDLL:

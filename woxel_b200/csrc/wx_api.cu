@@ -10,16 +10,23 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <exception>
+#include <memory>
 #include <new>
 #include <string>
 #include <thread>
 #include <vector>
+
+#include <nvtx3/nvToolsExt.h>  // header-only; a no-op unless a profiler injects the NVTX library
 
 #include "wx_device.cuh"
 #include "wx_internal.h"
 #include "wx_pack.h"
 
 using namespace wx;
+
+// Every entry point that allocates on the host (vectors, threads) is a function-try-block: no C++ exception crosses the C ABI
+// (bad_alloc -> WX_ERR_OUT_OF_MEMORY, anything else -> WX_ERR_UNSUPPORTED with the text in wx_last_error(NULL)).
 
 // ---------------------------------------------------------------------------------------------
 // Context
@@ -88,6 +95,20 @@ struct WxTree {
   bool grid_ok = true;        // ... and the index bases of the world grid fit 32 bits: march_grid applies
   int32_t bbox_cells[6] = {1 << 30, 1 << 30, 1 << 30, -1, -1, -1};  // grid_bbox_cells (tolerance-mode march)
   WxTreeInfo info{};
+};
+
+// NVTX range around a phase of an entry point (upload / sweep / render / read-back), only when WX_OPT_NVTX is set: the
+// reference's tracing hooks are its wgpu debug labels; these show up as named ranges in Nsight Systems.
+struct NvtxRange {
+  bool on;
+  NvtxRange(const WxContext* ctx, const char* name) : on(ctx && ctx->nvtx) {
+    if (on) nvtxRangePushA(name);
+  }
+  ~NvtxRange() {
+    if (on) nvtxRangePop();
+  }
+  NvtxRange(const NvtxRange&) = delete;
+  NvtxRange& operator=(const NvtxRange&) = delete;
 };
 
 static thread_local std::string g_last_error;  // failures before a context exists
@@ -211,7 +232,7 @@ extern "C" const char* wx_strerror(int status) {
 
 extern "C" const char* wx_last_error(const WxContext* ctx) { return ctx ? ctx->last_error.c_str() : g_last_error.c_str(); }
 
-extern "C" int wx_init(int n_devices, const int* device_ids, WxContext** out) {
+extern "C" int wx_init(int n_devices, const int* device_ids, WxContext** out) try {
   if (!out || n_devices < 0) return fail(nullptr, WX_ERR_INVALID_ARGUMENT, "wx_init: bad arguments");
   *out = nullptr;
   int count = 0;
@@ -276,6 +297,12 @@ extern "C" int wx_init(int n_devices, const int* device_ids, WxContext** out) {
   }
   *out = ctx;
   return WX_OK;
+} catch (const std::bad_alloc&) {
+  return fail(nullptr, WX_ERR_OUT_OF_MEMORY, "wx_init: host allocation failed");
+} catch (const std::exception& ex) {
+  return fail(nullptr, WX_ERR_UNSUPPORTED, std::string("wx_init: ") + ex.what());
+} catch (...) {
+  return fail(nullptr, WX_ERR_UNSUPPORTED, "wx_init: unexpected exception");
 }
 
 static void free_frame_buffers(WxContext* ctx) {
@@ -340,7 +367,7 @@ static WxTree* new_tree(WxContext* ctx, const WxTreeDesc* d, uint32_t leaf_bits,
   return t;
 }
 
-extern "C" int wx_tree_upload(WxContext* ctx, const WxTreeDesc* d, WxTree** out) {
+extern "C" int wx_tree_upload(WxContext* ctx, const WxTreeDesc* d, WxTree** out) try {
   if (!ctx || !d || !out) return fail(ctx, WX_ERR_INVALID_ARGUMENT, "wx_tree_upload: null argument");
   *out = nullptr;
   if ((d->n5 && (!d->origins || !d->kids5 || !d->vals5 || !d->tab5)) || (d->n4 && (!d->kids4 || !d->vals4 || !d->tab4)) ||
@@ -350,6 +377,8 @@ extern "C" int wx_tree_upload(WxContext* ctx, const WxTreeDesc* d, WxTree** out)
     return fail(ctx, WX_ERR_INVALID_ARGUMENT, "wx_tree_upload: tab3_elem_bytes must be 1 or 4");
   if (d->n5 > (uint32_t)kRootIndexMask || d->n4 >= kChildFlag || d->n3 >= kChildFlag)
     return fail(ctx, WX_ERR_UNSUPPORTED, "wx_tree_upload: too many nodes");  // 16383 N5s would be 2 GB of N5 tables alone
+  NvtxRange range_all(ctx, "wx_tree_upload");
+  std::unique_ptr<NvtxRange> range_pack(new (std::nothrow) NvtxRange(ctx, "wx_tree_upload: pack (host)"));
 
   std::vector<uint32_t> e5, e4;
   std::vector<uint8_t> l3;
@@ -364,6 +393,8 @@ extern "C" int wx_tree_upload(WxContext* ctx, const WxTreeDesc* d, WxTree** out)
   const uint32_t leaf_bits = pack_leaves(d->n3, d->vals3, d->tab3, d->tab3_elem_bytes, l3, &max3v);
 
   WxTree* t = new_tree(ctx, d, leaf_bits, max5, max4, max3v);
+  range_pack.reset();
+  NvtxRange range_up(ctx, "wx_tree_upload: H2D + world grid");
   if (!t) return fail(ctx, WX_ERR_OUT_OF_MEMORY, "wx_tree_upload: host allocation");
 
   auto up = [&](int dev_i) -> int {
@@ -401,6 +432,12 @@ extern "C" int wx_tree_upload(WxContext* ctx, const WxTreeDesc* d, WxTree** out)
   (void)cudaSetDevice(ctx->dev[0].id);
   *out = t;
   return WX_OK;
+} catch (const std::bad_alloc&) {
+  return fail(nullptr, WX_ERR_OUT_OF_MEMORY, "wx_tree_upload: host allocation failed");
+} catch (const std::exception& ex) {
+  return fail(nullptr, WX_ERR_UNSUPPORTED, std::string("wx_tree_upload: ") + ex.what());
+} catch (...) {
+  return fail(nullptr, WX_ERR_UNSUPPORTED, "wx_tree_upload: unexpected exception");
 }
 
 static int check_topology(WxContext* ctx, const WxTreeDesc* d, const char* who) {
@@ -412,7 +449,7 @@ static int check_topology(WxContext* ctx, const WxTreeDesc* d, const char* who) 
 }
 
 extern "C" int wx_compute_sdf(WxContext* ctx, const WxTreeDesc* d, uint32_t* tab5_out, uint32_t* tab4_out, void* tab3_out,
-                              uint32_t tab3_elem_bytes, WxSdfInfo* info) {
+                              uint32_t tab3_elem_bytes, WxSdfInfo* info) try {
   if (!ctx || !d) return fail(ctx, WX_ERR_INVALID_ARGUMENT, "wx_compute_sdf: null argument");
   if ((d->n5 && (!d->origins || !d->kids5 || !d->tab5 || !tab5_out)) || (d->n4 && (!d->kids4 || !d->tab4 || !tab4_out)) ||
       (d->n3 && (!d->vals3 || !tab3_out)))
@@ -420,6 +457,7 @@ extern "C" int wx_compute_sdf(WxContext* ctx, const WxTreeDesc* d, uint32_t* tab
   if (tab3_elem_bytes != 1 && tab3_elem_bytes != 4) return fail(ctx, WX_ERR_INVALID_ARGUMENT, "wx_compute_sdf: tab3_elem_bytes must be 1 or 4");
   // child indices must be in range: the sweeps follow them
   if (int bad = check_topology(ctx, d, "wx_compute_sdf")) return bad;
+  NvtxRange range(ctx, "wx_compute_sdf: sweep");
   DeviceSlot& d0 = ctx->dev[0];
   WX_CUDA(ctx, cudaSetDevice(d0.id));
   const auto t0 = std::chrono::steady_clock::now();
@@ -433,9 +471,15 @@ extern "C" int wx_compute_sdf(WxContext* ctx, const WxTreeDesc* d, uint32_t* tab
   }
   if (r[3]) return fail(ctx, WX_ERR_UNSUPPORTED, "wx_compute_sdf: a leaf distance does not fit the requested element size");
   return WX_OK;
+} catch (const std::bad_alloc&) {
+  return fail(nullptr, WX_ERR_OUT_OF_MEMORY, "wx_compute_sdf: host allocation failed");
+} catch (const std::exception& ex) {
+  return fail(nullptr, WX_ERR_UNSUPPORTED, std::string("wx_compute_sdf: ") + ex.what());
+} catch (...) {
+  return fail(nullptr, WX_ERR_UNSUPPORTED, "wx_compute_sdf: unexpected exception");
 }
 
-extern "C" int wx_tree_build(WxContext* ctx, const WxTreeDesc* d, WxTree** out, WxSdfInfo* info) {
+extern "C" int wx_tree_build(WxContext* ctx, const WxTreeDesc* d, WxTree** out, WxSdfInfo* info) try {
   if (!ctx || !d || !out) return fail(ctx, WX_ERR_INVALID_ARGUMENT, "wx_tree_build: null argument");
   *out = nullptr;
   if ((d->n5 && (!d->origins || !d->kids5 || !d->vals5 || !d->tab5)) || (d->n4 && (!d->kids4 || !d->vals4 || !d->tab4)) || (d->n3 && !d->vals3))
@@ -443,6 +487,7 @@ extern "C" int wx_tree_build(WxContext* ctx, const WxTreeDesc* d, WxTree** out, 
   if (d->n5 > (uint32_t)kRootIndexMask || d->n4 >= kChildFlag || d->n3 >= kChildFlag) return fail(ctx, WX_ERR_UNSUPPORTED, "wx_tree_build: too many nodes");
   int rc = check_topology(ctx, d, "wx_tree_build");
   if (rc) return rc;
+  NvtxRange range(ctx, "wx_tree_build: sweep + pack + replicate");
   const auto t0 = std::chrono::steady_clock::now();
   const size_t s5 = (size_t)d->n5 * 32768, s4 = (size_t)d->n4 * 4096, s3 = (size_t)d->n3 * 512;
   DeviceSlot& d0 = ctx->dev[0];
@@ -523,6 +568,12 @@ extern "C" int wx_tree_build(WxContext* ctx, const WxTreeDesc* d, WxTree** out, 
   if (info) info->total_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
   *out = t;
   return WX_OK;
+} catch (const std::bad_alloc&) {
+  return fail(nullptr, WX_ERR_OUT_OF_MEMORY, "wx_tree_build: host allocation failed");
+} catch (const std::exception& ex) {
+  return fail(nullptr, WX_ERR_UNSUPPORTED, std::string("wx_tree_build: ") + ex.what());
+} catch (...) {
+  return fail(nullptr, WX_ERR_UNSUPPORTED, "wx_tree_build: unexpected exception");
 }
 
 extern "C" int wx_tree_free(WxContext* ctx, WxTree* tree) {
@@ -633,12 +684,13 @@ static int check_render_args(WxContext* ctx, const WxTree* tree, const WxState* 
 
 extern "C" int wx_render_device(WxContext* ctx, int device_index, const WxTree* tree, const WxState* states, uint32_t n_states,
                                 uint32_t width, uint32_t height, uint8_t* rgba_dev, const WxAov* aov_dev, const WxShard* shard,
-                                void* stream) {
+                                void* stream) try {
   int rc = check_render_args(ctx, tree, states, n_states, width, height, rgba_dev);
   if (rc) return rc;
   if (device_index < 0 || device_index >= (int)ctx->dev.size()) return fail(ctx, WX_ERR_INVALID_ARGUMENT, "render: device index");
   if (!shard_ok(shard))
     return fail(ctx, WX_ERR_INVALID_ARGUMENT, "render: bad shard (band_rows must be a positive multiple of 8)");
+  NvtxRange range(ctx, "wx_render_device: launch");
   DeviceSlot& s = ctx->dev[device_index];
   WX_CUDA(ctx, cudaSetDevice(s.id));
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -654,6 +706,12 @@ extern "C" int wx_render_device(WxContext* ctx, int device_index, const WxTree* 
   ctx->info.launches = launches;
   ctx->info.rays = (uint64_t)(width / 8 * 8) * (height / 4 * 4) * n_states;  // whole frame; a shard renders its share
   return WX_OK;
+} catch (const std::bad_alloc&) {
+  return fail(nullptr, WX_ERR_OUT_OF_MEMORY, "wx_render_device: host allocation failed");
+} catch (const std::exception& ex) {
+  return fail(nullptr, WX_ERR_UNSUPPORTED, std::string("wx_render_device: ") + ex.what());
+} catch (...) {
+  return fail(nullptr, WX_ERR_UNSUPPORTED, "wx_render_device: unexpected exception");
 }
 
 static int ensure(WxContext* ctx, void** p, size_t* have, size_t need) {
@@ -796,7 +854,7 @@ static int gather_frame(WxContext* ctx) {
 }
 
 extern "C" int wx_render(WxContext* ctx, const WxTree* tree, const WxState* states, uint32_t n_states, uint32_t width,
-                         uint32_t height, uint8_t* rgba_out, const WxAov* aov_out) {
+                         uint32_t height, uint8_t* rgba_out, const WxAov* aov_out) try {
   int rc = check_render_args(ctx, tree, states, n_states, width, height, rgba_out);
   if (rc) return rc;
   const size_t npix = (size_t)n_states * width * height;
@@ -805,6 +863,8 @@ extern "C" int wx_render(WxContext* ctx, const WxTree* tree, const WxState* stat
   rc = ensure(ctx, (void**)&ctx->fb.rgba, &ctx->fb.rgba_bytes, npix * 4);
   if (rc) return rc;
   // AOV staging on device 0
+  NvtxRange range_all(ctx, "wx_render");
+  std::unique_ptr<NvtxRange> range_launch(new (std::nothrow) NvtxRange(ctx, "wx_render: launches (+ pipelined read-back)"));
   static const size_t aov_elem[8] = {1, 12, 4, 1, 4, 4, 1, 12};
   void* host_aov[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   WxAov dev_aov;
@@ -949,6 +1009,8 @@ extern "C" int wx_render(WxContext* ctx, const WxTree* tree, const WxState* stat
     WX_CUDA(ctx, cudaSetDevice(d0.id));
   }
   if (!copied) WX_CUDA(ctx, cudaMemcpyAsync(rgba_out, ctx->fb.rgba, npix * 4, cudaMemcpyDefault, d0.stream));
+  range_launch.reset();
+  NvtxRange range_rb(ctx, "wx_render: read-back + synchronize");
   for (int k = 0; k < 8; ++k)
     if (host_aov[k]) WX_CUDA(ctx, cudaMemcpyAsync(host_aov[k], ctx->fb.aov[k], npix * aov_elem[k], cudaMemcpyDeviceToHost, d0.stream));
   WX_CUDA(ctx, cudaEventRecord(ctx->total1, d0.stream));
@@ -961,6 +1023,51 @@ extern "C" int wx_render(WxContext* ctx, const WxTree* tree, const WxState* stat
   ctx->info.launches = launches;
   ctx->info.rays = (uint64_t)(width / 8 * 8) * (height / 4 * 4) * n_states;
   return WX_OK;
+} catch (const std::bad_alloc&) {
+  return fail(nullptr, WX_ERR_OUT_OF_MEMORY, "wx_render: host allocation failed");
+} catch (const std::exception& ex) {
+  return fail(nullptr, WX_ERR_UNSUPPORTED, std::string("wx_render: ") + ex.what());
+} catch (...) {
+  return fail(nullptr, WX_ERR_UNSUPPORTED, "wx_render: unexpected exception");
+}
+
+extern "C" int wx_render_shard(WxContext* ctx, const WxTree* tree, const WxState* states, uint32_t n_states, uint32_t width,
+                               uint32_t height, const WxShard* shard, uint8_t* rgba_out) try {
+  int rc = check_render_args(ctx, tree, states, n_states, width, height, rgba_out);
+  if (rc) return rc;
+  if (!shard || !shard_ok(shard) || shard->band_rows != (uint32_t)kBandRowsMultiple)
+    return fail(ctx, WX_ERR_INVALID_ARGUMENT, "wx_render_shard: a shard with band_rows == 8 is required");
+  NvtxRange range(ctx, "wx_render_shard: render + deliver rows");
+  const size_t npix = (size_t)n_states * width * height;
+  DeviceSlot& d0 = ctx->dev[0];
+  WX_CUDA(ctx, cudaSetDevice(d0.id));
+  rc = ensure(ctx, (void**)&ctx->fb.rgba, &ctx->fb.rgba_bytes, npix * 4);
+  if (rc) return rc;
+  WX_CUDA(ctx, cudaEventRecord(ctx->total0, d0.stream));
+  WX_CUDA(ctx, cudaEventRecord(d0.ev0, d0.stream));
+  uint32_t launches = 0;
+  rc = launch_on(ctx, 0, tree, states, n_states, width, height, ctx->fb.rgba, nullptr, shard, d0.stream, &launches);
+  if (rc) return rc;
+  WX_CUDA(ctx, cudaEventRecord(d0.ev1, d0.stream));
+  WX_CUDA(ctx, copy_own_bands(rgba_out, ctx->fb.rgba, (int)shard->index, (int)shard->count, 0, n_states, 0, height, width, height,
+                              cudaMemcpyDefault, d0.stream));
+  WX_CUDA(ctx, cudaEventRecord(ctx->total1, d0.stream));
+  WX_CUDA(ctx, cudaStreamSynchronize(d0.stream));
+  for (DeviceSlot& d : ctx->dev) d.events_pending = false;
+  d0.events_pending = true;
+  ctx->total_pending = true;
+  ctx->fb.rgba_valid = 0;  // only a shard's rows are valid: nothing for wx_capture_srgb
+  ctx->fb.distributed = false;
+  ctx->info = WxRenderInfo{};
+  ctx->info.launches = launches;
+  ctx->info.rays = (uint64_t)(width / 8 * 8) * (height / 4 * 4) * n_states;
+  return WX_OK;
+} catch (const std::bad_alloc&) {
+  return fail(nullptr, WX_ERR_OUT_OF_MEMORY, "wx_render_shard: host allocation failed");
+} catch (const std::exception& ex) {
+  return fail(nullptr, WX_ERR_UNSUPPORTED, std::string("wx_render_shard: ") + ex.what());
+} catch (...) {
+  return fail(nullptr, WX_ERR_UNSUPPORTED, "wx_render_shard: unexpected exception");
 }
 
 extern "C" int wx_set_option(WxContext* ctx, int option, int64_t value) {
@@ -1025,10 +1132,11 @@ extern "C" int wx_srgb_table(uint8_t table_out[256]) {
   return WX_OK;
 }
 
-extern "C" int wx_capture_srgb(WxContext* ctx, uint32_t n_states, uint32_t width, uint32_t height, uint8_t* rgb_out) {
+extern "C" int wx_capture_srgb(WxContext* ctx, uint32_t n_states, uint32_t width, uint32_t height, uint8_t* rgb_out) try {
   if (!ctx || !rgb_out) return fail(ctx, WX_ERR_INVALID_ARGUMENT, "wx_capture_srgb: null argument");
   const size_t npix = (size_t)n_states * width * height;
   if (npix == 0 || npix * 4 != ctx->fb.rgba_valid) return fail(ctx, WX_ERR_INVALID_ARGUMENT, "wx_capture_srgb: no frame of that size was rendered last");
+  NvtxRange range(ctx, "wx_capture_srgb");
   DeviceSlot& d0 = ctx->dev[0];
   WX_CUDA(ctx, cudaSetDevice(d0.id));
   int rc = gather_frame(ctx);
@@ -1039,9 +1147,15 @@ extern "C" int wx_capture_srgb(WxContext* ctx, uint32_t n_states, uint32_t width
   WX_CUDA(ctx, cudaMemcpyAsync(rgb_out, ctx->fb.rgb, npix * 3, cudaMemcpyDeviceToHost, d0.stream));
   WX_CUDA(ctx, cudaStreamSynchronize(d0.stream));
   return WX_OK;
+} catch (const std::bad_alloc&) {
+  return fail(nullptr, WX_ERR_OUT_OF_MEMORY, "wx_capture_srgb: host allocation failed");
+} catch (const std::exception& ex) {
+  return fail(nullptr, WX_ERR_UNSUPPORTED, std::string("wx_capture_srgb: ") + ex.what());
+} catch (...) {
+  return fail(nullptr, WX_ERR_UNSUPPORTED, "wx_capture_srgb: unexpected exception");
 }
 
-extern "C" int wx_last_render_info(const WxContext* cctx, WxRenderInfo* info) {
+extern "C" int wx_last_render_info(const WxContext* cctx, WxRenderInfo* info) try {
   WxContext* ctx = const_cast<WxContext*>(cctx);
   if (!ctx || !info) return WX_ERR_INVALID_ARGUMENT;
   float kmax = 0.f;
@@ -1064,6 +1178,12 @@ extern "C" int wx_last_render_info(const WxContext* cctx, WxRenderInfo* info) {
   (void)cudaSetDevice(ctx->dev[0].id);
   *info = ctx->info;
   return WX_OK;
+} catch (const std::bad_alloc&) {
+  return fail(nullptr, WX_ERR_OUT_OF_MEMORY, "wx_last_render_info: host allocation failed");
+} catch (const std::exception& ex) {
+  return fail(nullptr, WX_ERR_UNSUPPORTED, std::string("wx_last_render_info: ") + ex.what());
+} catch (...) {
+  return fail(nullptr, WX_ERR_UNSUPPORTED, "wx_last_render_info: unexpected exception");
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -98,9 +98,16 @@ extern "C" int64_t wxh_child_to_offset(int level, const uint32_t c[3]) {
 
 extern "C" WxhVdb* wxh_vdb_new(void) { return new (std::nothrow) WxhVdb(); }
 extern "C" void wxh_vdb_free(WxhVdb* v) { delete v; }
-extern "C" void wxh_vdb_set_voxel(WxhVdb* v, int32_t x, int32_t y, int32_t z, uint32_t value) { v->v.set_voxel({x, y, z}, value); }
+// void / pointer-returning entry points: no exception crosses the C ABI either -- a failure (out of host memory) leaves its
+// text in wxh_last_error() and, where there is a pointer to return, returns NULL.
+extern "C" void wxh_vdb_set_voxel(WxhVdb* v, int32_t x, int32_t y, int32_t z, uint32_t value) {
+  (void)guarded([&]() { return v->v.set_voxel({x, y, z}, value), 0; });
+}
 extern "C" void wxh_vdb_set_voxels(WxhVdb* v, const int32_t* xyz, size_t n, uint32_t value) {
-  for (size_t i = 0; i < n; ++i) v->v.set_voxel({xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]}, value);
+  (void)guarded([&]() {
+    for (size_t i = 0; i < n; ++i) v->v.set_voxel({xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]}, value);
+    return 0;
+  });
 }
 extern "C" int wxh_vdb_get_voxel(const WxhVdb* v, int32_t x, int32_t y, int32_t z, uint32_t* value, int* level) {
   const vdb::VdbEndpoint e = v->v.get_voxel({x, y, z});
@@ -113,12 +120,15 @@ extern "C" void wxh_vdb_count_nodes(const WxhVdb* v, uint64_t out[3]) {
   out[0] = c[0], out[1] = c[1], out[2] = c[2];
 }
 extern "C" uint64_t wxh_vdb_count_leaf_values(const WxhVdb* v) { return v->v.count_leaf_values(); }
-extern "C" void wxh_vdb_compute_sdf(WxhVdb* v) { v->v.compute_sdf(); }
+extern "C" void wxh_vdb_compute_sdf(WxhVdb* v) {
+  (void)guarded([&]() { return v->v.compute_sdf(), 0; });
+}
 
 extern "C" int wxh_blosc_decompress(const uint8_t* frame, size_t n, uint8_t* out, size_t cap, size_t* out_len) {
   if (!frame || !out_len || (!out && cap)) return WXH_ERR_INVALID_ARGUMENT;
   return guarded([&]() {
-    const std::vector<uint8_t> v = vdb::decompress_blosc_frame(frame, n);
+    *out_len = n >= 16 ? ((size_t)frame[4] | ((size_t)frame[5] << 8) | ((size_t)frame[6] << 16) | ((size_t)frame[7] << 24)) : 0;  // room needed, per the header
+    const std::vector<uint8_t> v = vdb::decompress_blosc_frame(frame, n, cap);  // refuses before allocating when the header claims more than cap
     *out_len = v.size();
     if (v.size() > cap) return (int)WXH_ERR_INVALID_ARGUMENT;  // *out_len says how much room is needed
     if (!v.empty()) memcpy(out, v.data(), v.size());
@@ -157,7 +167,7 @@ extern "C" int wxh_vdb_read(const char* path, const char* grid_name, WxhVdb** ou
 
 extern "C" WxhFlat* wxh_vdb_to_flat(const WxhVdb* v, int narrow_leaves) {
   WxhFlat* f = new (std::nothrow) WxhFlat();
-  if (f) f->f = v->v.to_flat(narrow_leaves != 0);
+  if (f && guarded([&]() { return f->f = v->v.to_flat(narrow_leaves != 0), 0; }) != 0) delete f, f = nullptr;
   return f;
 }
 extern "C" void wxh_flat_free(WxhFlat* f) { delete f; }
@@ -165,17 +175,17 @@ extern "C" void wxh_flat_desc(const WxhFlat* f, WxTreeDesc* out) { *out = f->f.d
 
 extern "C" WxhVdb* wxh_build_sphere(int32_t half, double radius, double band) {
   WxhVdb* v = new (std::nothrow) WxhVdb();
-  if (v) v->v = procedural::sphere_shell(half, radius, band);
+  if (v && guarded([&]() { return v->v = procedural::sphere_shell(half, radius, band), 0; }) != 0) delete v, v = nullptr;
   return v;
 }
 extern "C" WxhVdb* wxh_build_torus(int32_t half, double major, double minor, double band) {
   WxhVdb* v = new (std::nothrow) WxhVdb();
-  if (v) v->v = procedural::torus_shell(half, major, minor, band);
+  if (v && guarded([&]() { return v->v = procedural::torus_shell(half, major, minor, band), 0; }) != 0) delete v, v = nullptr;
   return v;
 }
 extern "C" WxhVdb* wxh_build_fog(int32_t half, double tau, double* occupancy) {
   WxhVdb* v = new (std::nothrow) WxhVdb();
-  if (v) v->v = procedural::fbm_fog(half, tau, occupancy);
+  if (v && guarded([&]() { return v->v = procedural::fbm_fog(half, tau, occupancy), 0; }) != 0) delete v, v = nullptr;
   return v;
 }
 

@@ -174,7 +174,7 @@ struct ArchiveHeader {
 // Blosc(LZ4, BloscLZ, zlib codecs; byte shuffle) block compression, active-mask compression,
 // half-float storage.
 // Decodes one c-blosc 1.x frame (BloscLZ / LZ4 / zlib codec, byte or bit shuffle); throws VdbError.
-std::vector<uint8_t> decompress_blosc_frame(const uint8_t* frame, size_t n);
+std::vector<uint8_t> decompress_blosc_frame(const uint8_t* frame, size_t n, size_t max_bytes = (size_t)-1);
 
 class VdbReader {
  public:

@@ -246,13 +246,21 @@ void bit_unshuffle_block(const uint8_t* in, uint8_t* out, size_t bsize, size_t t
   memcpy(out + ne8 * typesize, in + ne8 * typesize, bsize - ne8 * typesize);
 }
 
-std::vector<uint8_t> blosc_decompress(const uint8_t* f, size_t n) {
+// expected: the size the caller knows the frame must decode to (count * element size), or kAnySize.  Checked BEFORE anything is
+// allocated: the header of a crafted 16-byte frame may claim 4 GiB.  max_bytes: the most the caller has room for.
+constexpr size_t kAnySize = (size_t)-1;
+std::vector<uint8_t> blosc_decompress(const uint8_t* f, size_t n, size_t expected = kAnySize, size_t max_bytes = kAnySize) {
   auto bad = [](const char* what) { return VdbError(VdbError::InvalidBloscData, std::string("Blosc frame: ") + what); };
   auto le32 = [&](size_t at) { return (uint32_t)f[at] | ((uint32_t)f[at + 1] << 8) | ((uint32_t)f[at + 2] << 16) | ((uint32_t)f[at + 3] << 24); };
   if (n < 16) throw bad("shorter than its header");
   const uint8_t flags = f[2];
   const size_t typesize = f[3] ? f[3] : 1, nbytes = le32(4), blocksize = le32(8), cbytes = le32(12);
   if (cbytes > n) throw bad("cbytes exceeds the stored size");
+  if (expected != kAnySize && nbytes != expected) throw bad("decodes to an unexpected size");
+  if (nbytes > max_bytes) throw VdbError(VdbError::InvalidBloscData, "Blosc frame: needs " + std::to_string(nbytes) + " bytes of room");
+  // a stream cannot expand by more than the codecs' run-length limits (LZ4 / BloscLZ: < 256x, zlib: ~1030x): a header that
+  // claims more than that from n stored bytes is corrupt
+  if (nbytes / 1100 > n) throw bad("claims more data than its streams can hold");
   std::vector<uint8_t> out(nbytes);
   if (nbytes == 0) return out;
   if (flags & 0x2) {  // memcpyed
@@ -268,7 +276,7 @@ std::vector<uint8_t> blosc_decompress(const uint8_t* f, size_t n) {
   const size_t nblocks = (nbytes + blocksize - 1) / blocksize;
   if (n < 16 + 4 * nblocks) throw bad("block offsets are cut off");
   const bool may_split = !(flags & 0x10) && typesize <= 16 && blocksize / typesize >= 128;
-  std::vector<uint8_t> tmp(blocksize);
+  std::vector<uint8_t> tmp(std::min(blocksize, nbytes));  // a block never holds more than the data (the header's block size may claim 4 GiB)
   for (size_t b = 0; b < nblocks; ++b) {
     const size_t bsize = std::min(blocksize, nbytes - b * blocksize);
     const bool leftover = bsize < blocksize;
@@ -324,7 +332,7 @@ struct NodeValueReader {
         c.bytes(out.data(), out.size());
       } else {
         c.need((size_t)n);
-        out = blosc_decompress(c.b.data() + c.pos, (size_t)n);
+        out = blosc_decompress(c.b.data() + c.pos, (size_t)n, count * elem);
         if (out.size() != count * elem) throw VdbError(VdbError::InvalidBloscData, "Blosc block decodes to an unexpected size");
         c.pos += (size_t)n;
       }
@@ -498,6 +506,8 @@ VDB345 VdbReader::read_vdb345_grid(const std::string& name) {  // read.rs:123-14
 }
 
 // One Blosc frame, outside a file (tests; tools that meet Blosc buffers elsewhere).
-std::vector<uint8_t> decompress_blosc_frame(const uint8_t* frame, size_t n) { return blosc_decompress(frame, n); }
+std::vector<uint8_t> decompress_blosc_frame(const uint8_t* frame, size_t n, size_t max_bytes) {
+  return blosc_decompress(frame, n, kAnySize, max_bytes);
+}
 
 }  // namespace woxel::vdb

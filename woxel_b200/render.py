@@ -141,6 +141,14 @@ class Context:
         arr = (_ffi.WxState * len(states))(*states)
         self.check(_ffi.cuda_lib().wx_render(self._h, tree._h, arr, len(states), width, height, C.c_void_p(dst_ptr), None))
 
+    def render_shard_to(self, tree: "Tree", states, width: int, height: int, shard: tuple, dst_ptr: int) -> None:
+        """wx_render_shard: the rows of shard (index, count) of every frame, delivered to the frame stack at the raw address
+        dst_ptr (host memory or device memory of any GPU).  Blocking."""
+        states = list(states) if isinstance(states, (list, tuple)) else [states]
+        arr = (_ffi.WxState * len(states))(*states)
+        sh = _ffi.WxShard(shard[0], shard[1], 8, 0)
+        self.check(_ffi.cuda_lib().wx_render_shard(self._h, tree._h, arr, len(states), width, height, C.byref(sh), C.c_void_p(dst_ptr)))
+
     def compute_sdf(self, flat_or_desc, narrow_leaves: bool = False):
         """wx_compute_sdf: VDB345::compute_sdf (vdb345.rs:290-628) on the GPU for a flat tree (its tile / voxel
         distances are ignored on input).  Returns (tab5, tab4, tab3, WxSdfInfo) in the layout of FlatTree."""
