@@ -159,7 +159,18 @@ def test_config4_fog_1024_cubed_4k_against_the_oracle(gpu_ctx):
         tree.free()
 
 
-@pytest.mark.skipif(os.environ.get("WX_TEST_FULL_FOG") != "1", reason="needs ~40 GB of host memory for the oracle's tables: opt-in (WX_TEST_FULL_FOG=1); run once per round by tools/gpu/r2_config45.sh, result in profiles/")
+def _mem_available_gb() -> float:
+    try:
+        for line in open("/proc/meminfo"):
+            if line.startswith("MemAvailable:"):
+                return int(line.split()[1]) / 1e6
+    except OSError:
+        pass
+    return 0.0
+
+
+@pytest.mark.skipif(os.environ.get("WX_TEST_FULL_FOG") != "1" and _mem_available_gb() < 96.0,
+                    reason="needs ~40 GB of host memory for the oracle's tables: runs on boxes with >= 96 GB available, or with WX_TEST_FULL_FOG=1")
 def test_config4_fog_2048_cubed_4k_against_the_oracle(gpu_ctx):
     """BASELINE config 4 at its full 2048^3 (7.4 M leaves): one 4K frame from the outside camera against the oracle renderer."""
     half, w, h = 1024, 3840, 2160

@@ -29,12 +29,25 @@ constexpr int kThreads = 32 * WX_CTA_WARPS;
 #define WX_MIN_BLOCKS (36 / WX_CTA_WARPS)  // resident CTAs per SM the register budget is capped for (36 warps -> 56 registers)
 #endif
 
+// Launch order.  The hardware starts the CTAs of a grid in linear order (x fastest) and a launch ends with a drain as long as
+// its slowest remaining warp (a lone 355-step ray runs ~75 us).  The longest rays of a frame graze the
+// silhouette of what is in view, which for a framed object lies towards the border of the image; the centre holds short, early
+// hits.  So tiles are taken from the outside in -- columns 0, n-1, 1, n-2, ... and rows likewise: the slow rays start first and
+// the grid ends on the cheap centre tiles.  Only the order changes, not which pixel a thread renders (WX_NO_OUTSIDE_IN: A/B).
+__device__ __forceinline__ uint32_t outside_in(uint32_t i, uint32_t n) {
+#ifdef WX_NO_OUTSIDE_IN
+  return i;
+#else
+  return (i & 1u) ? n - 1u - (i >> 1) : (i >> 1);
+#endif
+}
+
 // Tiled kernel: one thread per pixel of the grid, a warp per 4x8-pixel tile, a CTA per four tiles (16x8 pixels).
 template <int MODE, bool AOV>
 __global__ void __launch_bounds__(kThreads, WX_MIN_BLOCKS) raycast_kernel(const __grid_constant__ RenderParams P) {
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t tx = blockIdx.x;
-  const uint32_t trow = blockIdx.y;                             // tile row among the rows this launch owns
+  const uint32_t tx = outside_in(blockIdx.x, gridDim.x);
+  const uint32_t trow = outside_in(blockIdx.y, gridDim.y);      // tile row among the rows this launch owns
   // band of this tile row and the row inside it; the two usual shapes (one band, or one tile row per band) need no division
   uint32_t own_band = 0, in_band = trow;
   if (P.tile_rows_per_band == 1u) own_band = trow, in_band = 0;
@@ -54,12 +67,13 @@ __global__ void __launch_bounds__(kThreads, WX_MIN_BLOCKS) raycast_kernel(const 
 template <int MODE, bool AOV>
 __global__ void __launch_bounds__(kThreads, WX_MIN_BLOCKS) raycast_kernel_tol(const __grid_constant__ RenderParams P) {
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  uint32_t own_band = 0, in_band = blockIdx.y;
-  if (P.tile_rows_per_band == 1u) own_band = blockIdx.y, in_band = 0;
-  else if (P.own_bands > 1u) own_band = blockIdx.y / P.tile_rows_per_band, in_band = blockIdx.y - own_band * P.tile_rows_per_band;
+  const uint32_t tx = outside_in(blockIdx.x, gridDim.x), trow = outside_in(blockIdx.y, gridDim.y);
+  uint32_t own_band = 0, in_band = trow;
+  if (P.tile_rows_per_band == 1u) own_band = trow, in_band = 0;
+  else if (P.own_bands > 1u) own_band = trow / P.tile_rows_per_band, in_band = trow - own_band * P.tile_rows_per_band;
   const uint32_t band = own_band * P.shard_count + P.shard_index;
   PixelRef q;
-  q.x = blockIdx.x * kTileW + WX_LANE_X(warp, lane);
+  q.x = tx * kTileW + WX_LANE_X(warp, lane);
   q.y = P.row_base + band * P.band_rows + in_band * kTileH + WX_LANE_Y(warp, lane);
   q.cam = P.cam_base + blockIdx.z;
   q.in_frame = q.x < P.width && q.y < P.row_end;
