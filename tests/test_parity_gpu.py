@@ -248,8 +248,8 @@ def test_pipelined_readback_equals_single_launch(gpu_ctx):
     for mode in (0, 3):
         st = scenes.state_for(eye, target, w, h, mode=mode)
         plain, _ = gpu_ctx.render(tree, to_wx(st), w, h)           # chunked + pipelined
-        single, _ = gpu_ctx.render(tree, to_wx(st), w, h, aov=True)  # one launch
-        assert gpu_ctx.last_render_info().launches == 1
+        single, _ = gpu_ctx.render(tree, to_wx(st), w, h, aov=True)  # one launch (+ the long-tile kernel once this geometry has run before)
+        assert gpu_ctx.last_render_info().launches in (1, 2)
         assert np.array_equal(plain, single)
         ref, _, _ = scenes.get_scene(name).gpu.render(st, w, h, aov=False)
         assert np.array_equal(plain[0], ref)

@@ -210,3 +210,56 @@ def test_config5_orbit_64_cameras_1080p_against_the_oracle(gpu_ctx):
             assert np.array_equal(one[0], batch[k]), k
     finally:
         tree.free()
+
+
+def test_long_tiles_first_changes_no_pixel(gpu_ctx):
+    """WX_OPT_LONG_FIRST (default on): from the second launch of a frame geometry on, the tiles that held long rays in the launch
+    before are rendered by a small kernel that starts first and the main grid skips them.  Every pixel must still be written
+    exactly once: frames rendered 1st / 2nd / 3rd time, with the camera changing in between (the list then describes another
+    view), as a camera batch, sharded, and with the option off are all equal to the oracle's."""
+    name, w, h = "icosahedron", 1280, 720
+    s = scenes.get_scene(name)
+    tree = gpu_ctx.upload(s.desc())
+    cams = [scenes.CAMERAS["oblique_a"], scenes.CAMERAS["default"], scenes.CAMERAS["oblique_b"]]
+    sts = [scenes.state_for(*c, w, h, mode=2) for c in cams]  # mode 2: the colour is the iteration count
+    refs = [s.gpu.render(st, w, h, aov=False)[0] for st in sts]
+    lib = _ffi.cuda_lib()
+    buf = C.c_void_p()
+    gpu_ctx.check(lib.wx_device_alloc(gpu_ctx._h, 0, w * h * 4, C.byref(buf)))
+
+    def device_frame(st, shard=None):
+        gpu_ctx.render_device(tree, to_wx(st), w, h, buf.value, shard=shard)
+        out = np.zeros((h, w, 4), np.uint8)
+        gpu_ctx.check(lib.wx_stream_synchronize(gpu_ctx._h, 0, None))
+        gpu_ctx.check(lib.wx_memcpy_d2h(gpu_ctx._h, 0, out.ctypes.data, buf, w * h * 4, None))
+        gpu_ctx.check(lib.wx_stream_synchronize(gpu_ctx._h, 0, None))
+        return out
+
+    try:
+        assert gpu_ctx.get_option(_ffi.WX_OPT_LONG_FIRST) == 1
+        for rep in range(3):
+            for k in (0, 1, 2, 2, 0):  # same geometry key, the camera changes under the list
+                assert np.array_equal(device_frame(sts[k]), refs[k]), (rep, k)
+        launches = gpu_ctx.last_render_info().launches
+        assert launches == 2, "the long-tile kernel did not run"
+        batch, _ = gpu_ctx.render(tree, [to_wx(st) for st in sts], w, h)
+        batch2, _ = gpu_ctx.render(tree, [to_wx(st) for st in sts], w, h)
+        for k in range(3):
+            assert np.array_equal(batch[k], refs[k]) and np.array_equal(batch2[k], refs[k])
+        # shards: each shard's own rows only, twice
+        for rep in range(2):
+            gpu_ctx.render_device(tree, to_wx(sts[0]), w, h, buf.value)  # whole frame first, then overwrite by shards of another camera
+            for i in range(3):
+                gpu_ctx.render_device(tree, to_wx(sts[1]), w, h, buf.value, shard=(i, 3, 8))
+            out = np.zeros((h, w, 4), np.uint8)
+            gpu_ctx.check(lib.wx_stream_synchronize(gpu_ctx._h, 0, None))
+            gpu_ctx.check(lib.wx_memcpy_d2h(gpu_ctx._h, 0, out.ctypes.data, buf, w * h * 4, None))
+            gpu_ctx.check(lib.wx_stream_synchronize(gpu_ctx._h, 0, None))
+            assert np.array_equal(out, refs[1]), rep
+        gpu_ctx.set_option(_ffi.WX_OPT_LONG_FIRST, 0)
+        assert np.array_equal(device_frame(sts[0]), refs[0])
+        assert gpu_ctx.last_render_info().launches == 1
+    finally:
+        gpu_ctx.set_option(_ffi.WX_OPT_LONG_FIRST, 1)
+        gpu_ctx.check(lib.wx_device_free(gpu_ctx._h, 0, buf))
+        tree.free()

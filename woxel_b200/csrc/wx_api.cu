@@ -33,8 +33,94 @@ using namespace wx;
 // ---------------------------------------------------------------------------------------------
 constexpr uint32_t kCounterRing = 256;  // launches that may be in flight on one device before a counter is reused
 
+// Long-tiles-first state (wx_internal.h TileSched) of ONE launch geometry on ONE stream: two sets of (list, flags), the
+// previous launch's and the one being recorded, swapped after every launch; a high-priority stream for the long-tile kernel.
+// Everything a launch touches is ordered on the launch's stream, so launches of the same geometry on the same stream never
+// race; other streams / geometries get their own entry.
+struct SchedKey {
+  const void* tree;
+  const void* stream;
+  uint32_t width, height, cam0, ncam, shard_index, shard_count, band_rows, row0, row1;
+  bool operator==(const SchedKey& o) const { return memcmp(this, &o, sizeof(*this)) == 0; }
+};
+struct SchedEntry final : TileSched {
+  SchedKey key{};
+  uint32_t* list[2] = {nullptr, nullptr};
+  uint32_t* flag[2] = {nullptr, nullptr};
+  uint32_t n_tiles = 0, cap = 0;
+  int cur = 0;
+  bool valid = false;  // set `cur` describes a finished launch of this geometry
+  cudaStream_t ls = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+  uint64_t last_use = 0;
+
+  void release() {
+    if (ls) (void)cudaStreamSynchronize(ls);
+    for (int k = 0; k < 2; ++k) {
+      if (list[k]) (void)cudaFree(list[k]);
+      if (flag[k]) (void)cudaFree(flag[k]);
+      list[k] = flag[k] = nullptr;
+    }
+    n_tiles = cap = 0, valid = false;
+  }
+  ~SchedEntry() override {
+    release();
+    if (ls) (void)cudaStreamDestroy(ls);
+    if (fork) (void)cudaEventDestroy(fork);
+    if (join) (void)cudaEventDestroy(join);
+  }
+  cudaError_t prepare(RenderParams& P, uint32_t n_cams, uint32_t tiles, cudaStream_t stream, cudaStream_t* long_stream) override {
+    *long_stream = nullptr;
+    cudaError_t e = cudaSuccess;
+    if (!ls) {
+      int lo = 0, hi = 0;
+      (void)cudaDeviceGetStreamPriorityRange(&lo, &hi);
+      e = cudaStreamCreateWithPriority(&ls, cudaStreamNonBlocking, hi);
+      if (e == cudaSuccess) e = cudaEventCreateWithFlags(&fork, cudaEventDisableTiming);
+      if (e == cudaSuccess) e = cudaEventCreateWithFlags(&join, cudaEventDisableTiming);
+      if (e != cudaSuccess) return e;
+    }
+    if (tiles != n_tiles) {
+      release();
+      n_tiles = tiles, cap = std::min<uint32_t>(std::max<uint32_t>(tiles / 16u, 64u), 4096u);
+      for (int k = 0; k < 2 && e == cudaSuccess; ++k) {
+        e = cudaMalloc(&list[k], ((size_t)cap + 1) * 4);
+        if (e == cudaSuccess) e = cudaMalloc(&flag[k], (size_t)n_tiles * 4);
+      }
+      if (e != cudaSuccess) {
+        release();
+        return e;
+      }
+    }
+    const int nxt = cur ^ 1;
+    e = cudaMemsetAsync(flag[nxt], 0, (size_t)n_tiles * 4, stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(list[nxt], 0, 4, stream);
+    if (e != cudaSuccess) return e;
+    P.next_list = list[nxt], P.next_flag = flag[nxt];
+    P.sched_cap = cap, P.sched_threshold = 96u;  // ~3x the mean primary ray of the benchmark scenes (20-50 iterations)
+    P.prev_list = nullptr, P.prev_flag = nullptr;
+    if (valid) {
+      P.prev_list = list[cur], P.prev_flag = flag[cur];
+      e = cudaEventRecord(fork, stream);
+      if (e == cudaSuccess) e = cudaStreamWaitEvent(ls, fork, 0);
+      if (e != cudaSuccess) return e;
+      *long_stream = ls;
+    }
+    return cudaSuccess;
+  }
+  cudaError_t finish(cudaStream_t stream) override {
+    cudaError_t e = cudaEventRecord(join, ls);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(stream, join, 0);
+    return e;
+  }
+  void launched() { cur ^= 1, valid = true; }  // the set just recorded becomes "previous"
+};
+constexpr size_t kSchedEntries = 24;
+
 struct DeviceSlot {
   int id = 0;
+  std::vector<std::shared_ptr<SchedEntry>> sched;  // long-tiles-first state per (geometry, stream)
+  uint64_t sched_clock = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool events_pending = false;
@@ -321,6 +407,8 @@ extern "C" int wx_shutdown(WxContext* ctx) {
   for (DeviceSlot& s : ctx->dev) {
     (void)cudaSetDevice(s.id);
     if (s.stream) (void)cudaStreamSynchronize(s.stream);
+    (void)cudaDeviceSynchronize();
+    s.sched.clear();
     if (s.d_states) (void)cudaFree(s.d_states);
     if (s.scratch) (void)cudaFree(s.scratch);
     if (s.counters) (void)cudaFree(s.counters);
@@ -655,7 +743,31 @@ static int launch_on(WxContext* ctx, int dev_i, const WxTree* tree, const WxStat
     P.row_base = row0, P.row_end = row1;
     uint32_t l = 0;
     uint32_t* counter = s.counters + (s.counter_next++ % kCounterRing);
-    const cudaError_t le = launch_raycast(P, e - b, mode, stream, &l, counter, s.resident_ctas, ctx->opt);
+    // long-tiles-first state of this launch geometry on this stream (plain launches when the option is off)
+    SchedEntry* se = nullptr;
+    P.prev_list = nullptr, P.prev_flag = nullptr, P.next_list = nullptr, P.next_flag = nullptr;
+    if (ctx->opt.long_first && ctx->opt.kernel == 0) {
+      SchedKey key;
+      memset(&key, 0, sizeof(key));
+      key.tree = tree, key.stream = stream, key.width = width, key.height = height, key.cam0 = b, key.ncam = e - b;
+      key.shard_index = P.shard_index, key.shard_count = P.shard_count, key.band_rows = P.band_rows, key.row0 = row0, key.row1 = row1;
+      for (auto& c : s.sched)
+        if (c->key == key) se = c.get();
+      if (!se) {
+        if (s.sched.size() >= kSchedEntries) {  // evict the entry used longest ago
+          size_t victim = 0;
+          for (size_t k = 1; k < s.sched.size(); ++k)
+            if (s.sched[k]->last_use < s.sched[victim]->last_use) victim = k;
+          s.sched.erase(s.sched.begin() + (long)victim);
+        }
+        s.sched.emplace_back(new SchedEntry());
+        se = s.sched.back().get();
+        se->key = key;
+      }
+      se->last_use = ++s.sched_clock;
+    }
+    const cudaError_t le = launch_raycast(P, e - b, mode, stream, &l, counter, s.resident_ctas, ctx->opt, se);
+    if (le == cudaSuccess && se && P.next_list) se->launched();
     if (le != cudaSuccess) {
       if (launch_states) (void)cudaFreeAsync(launch_states, stream);
       return fail_cuda(ctx, le, "launch_raycast");
@@ -1093,6 +1205,10 @@ extern "C" int wx_set_option(WxContext* ctx, int option, int64_t value) {
       if (value != 0 && value != 1) break;
       ctx->nvtx = value != 0;
       return WX_OK;
+    case WX_OPT_LONG_FIRST:
+      if (value != 0 && value != 1) break;
+      ctx->opt.long_first = (int)value;
+      return WX_OK;
     default:
       return fail(ctx, WX_ERR_INVALID_ARGUMENT, "wx_set_option: unknown option");
   }
@@ -1107,6 +1223,7 @@ extern "C" int wx_get_option(const WxContext* ctx, int option, int64_t* value_ou
     case WX_OPT_RENDER_CHUNKS: *value_out = ctx->render_chunks; return WX_OK;
     case WX_OPT_SMEM_PAD: *value_out = (int64_t)ctx->opt.smem_pad; return WX_OK;
     case WX_OPT_NVTX: *value_out = ctx->nvtx ? 1 : 0; return WX_OK;
+    case WX_OPT_LONG_FIRST: *value_out = ctx->opt.long_first; return WX_OK;
     default: return WX_ERR_INVALID_ARGUMENT;
   }
 }

@@ -163,6 +163,15 @@ struct RenderParams {
   uchar4* rgba;
   AovPtrs aov;
   uint32_t has_aov;
+  // Long tiles first (wx_raycast.cu): the tiles (CTA footprints) of the PREVIOUS launch with this geometry that held a ray of at
+  // least sched_threshold iterations -- prev_list[0] = how many, prev_list[1..] their ids, prev_flag[tile] = 1 for each -- are
+  // rendered by a small kernel that starts first; the main grid skips them.  Every launch records the same for the next one
+  // (next_list / next_flag, zeroed beforehand).  All null / 0: plain launch.
+  const uint32_t* prev_list;
+  const uint32_t* prev_flag;
+  uint32_t* next_list;
+  uint32_t* next_flag;
+  uint32_t sched_cap, sched_threshold;
 };
 // MARCH template parameter of the kernels: how hdda_ray is evaluated (WX_OPT_MARCH)
 constexpr int kMarchExact = 0, kMarchTolerance = 1;
@@ -1015,9 +1024,11 @@ __device__ __forceinline__ void shade_and_store(const RenderParams& P, const Pix
 }
 
 // cp_main (:60-68) for one pixel: ray generation, hdda_ray, ray_trace, store.
+// Returns the iteration count of the primary ray (0 for pixels outside the frame / the dispatch): the cost the launcher's
+// long-tiles-first list is built from.
 template <int MODE, bool AOV, int MARCH = kMarchExact>
-__device__ __forceinline__ void render_pixel(const RenderParams& P, const PixelRef& q) {
-  if (!q.in_frame) return;
+__device__ __forceinline__ uint32_t render_pixel(const RenderParams& P, const PixelRef& q) {
+  if (!q.in_frame) return 0u;
   if (!q.dispatched) {  // never dispatched by the reference: zero-initialised texel (and zeroed AOVs)
     const size_t pix = ((size_t)q.cam * P.height + q.y) * P.width + q.x;
     P.rgba[pix] = make_uchar4(0, 0, 0, 0);
@@ -1032,7 +1043,7 @@ __device__ __forceinline__ void render_pixel(const RenderParams& P, const PixelR
       if (a.mask) a.mask[pix] = 0;
       if (a.pos) a.pos[3 * pix + 0] = a.pos[3 * pix + 1] = a.pos[3 * pix + 2] = 0.f;
     }
-    return;
+    return 0u;
   }
   // the ray basis: from the constant bank for a single state (the usual frame), else from the batch in global memory
   V3 u, mv, wp, eye;
@@ -1046,7 +1057,9 @@ __device__ __forceinline__ void render_pixel(const RenderParams& P, const PixelR
   }
   const float px = (float)q.x + 0.001f, py = (float)q.y + 0.001f;
   const V3 dir = normalize3((px * u + py * mv) + wp);
-  shade_and_store<MODE, AOV, MARCH>(P, q, hdda_ray<MARCH>(P.tree, eye, dir), dir);
+  const HitOut hit = hdda_ray<MARCH>(P.tree, eye, dir);
+  shade_and_store<MODE, AOV, MARCH>(P, q, hit, dir);
+  return hit.i;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -18,9 +18,17 @@ struct LaunchOptions {
   int kernel = 0;        // WX_OPT_KERNEL: 0 tiled grid, 1 warp-level tile queue, 2 CTA-level chunk queue
   size_t smem_pad = 0;   // WX_OPT_SMEM_PAD
   int march = 0;         // WX_OPT_MARCH: 0 exact, 1 tolerance mode
+  int long_first = 1;    // WX_OPT_LONG_FIRST: tiles that held long rays in the previous launch of the same geometry start first
+};
+
+// Long-tiles-first state of one launch geometry on one stream (wx_api.cu owns the objects; wx_raycast.cu drives them).
+struct TileSched {
+  virtual cudaError_t prepare(RenderParams& P, uint32_t n_cams, uint32_t n_tiles, cudaStream_t stream, cudaStream_t* long_stream) = 0;
+  virtual cudaError_t finish(cudaStream_t stream) = 0;
+  virtual ~TileSched() {}
 };
 cudaError_t launch_raycast(RenderParams& P, uint32_t n_cams, uint32_t render_mode, cudaStream_t stream, uint32_t* launches,
-                           uint32_t* work_counter, uint32_t resident_ctas, const LaunchOptions& opt);
+                           uint32_t* work_counter, uint32_t resident_ctas, const LaunchOptions& opt, TileSched* sched = nullptr);
 constexpr uint32_t kCtasPerSm = 9;
 // RGBA8 (linear) -> RGB8 through recorder.rs' linear_to_srgb; rgba_dev must be 16-byte aligned, rgb_dev 4-byte aligned.
 cudaError_t launch_srgb_rgb8(const uint8_t* rgba_dev, uint8_t* rgb_dev, size_t n_pixels, cudaStream_t stream);

@@ -42,12 +42,11 @@ __device__ __forceinline__ uint32_t outside_in(uint32_t i, uint32_t n) {
 #endif
 }
 
-// Tiled kernel: one thread per pixel of the grid, a warp per 4x8-pixel tile, a CTA per four tiles (16x8 pixels).
-template <int MODE, bool AOV>
-__global__ void __launch_bounds__(kThreads, WX_MIN_BLOCKS) raycast_kernel(const __grid_constant__ RenderParams P) {
+// One CTA's tile: tile column tx, tile row trow among the rows this launch owns, camera cam_i of the launch.  Tile id =
+// (cam_i * tile_rows + trow) * tiles_x + tx.  Records the tile for the next launch's long list when one of its rays was long.
+template <int MODE, bool AOV, int MARCH>
+__device__ __forceinline__ void render_tile(const RenderParams& P, uint32_t tx, uint32_t trow, uint32_t cam_i, uint32_t tile_id) {
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t tx = outside_in(blockIdx.x, gridDim.x);
-  const uint32_t trow = outside_in(blockIdx.y, gridDim.y);      // tile row among the rows this launch owns
   // band of this tile row and the row inside it; the two usual shapes (one band, or one tile row per band) need no division
   uint32_t own_band = 0, in_band = trow;
   if (P.tile_rows_per_band == 1u) own_band = trow, in_band = 0;
@@ -56,29 +55,59 @@ __global__ void __launch_bounds__(kThreads, WX_MIN_BLOCKS) raycast_kernel(const 
   PixelRef q;
   q.x = tx * kTileW + WX_LANE_X(warp, lane);
   q.y = P.row_base + band * P.band_rows + in_band * kTileH + WX_LANE_Y(warp, lane);
-  q.cam = P.cam_base + blockIdx.z;
+  q.cam = P.cam_base + cam_i;
   q.in_frame = q.x < P.width && q.y < P.row_end;
   q.dispatched = q.x < P.disp_w && q.y < P.disp_h;
-  render_pixel<MODE, AOV>(P, q);
+  const uint32_t iters = render_pixel<MODE, AOV, MARCH>(P, q);
+  if (P.next_flag != nullptr && iters >= P.sched_threshold) {  // a long ray: this tile starts first next time (few lanes get here)
+    if (atomicExch(P.next_flag + tile_id, 1u) == 0u) {
+      const uint32_t slot = atomicAdd(P.next_list, 1u);
+      if (slot < P.sched_cap) P.next_list[1u + slot] = tile_id;
+      else P.next_flag[tile_id] = 0u;  // list full: the tile stays in the main grid
+    }
+  }
 }
 
-// The same kernel in tolerance mode (WX_OPT_MARCH = 1, wx_device.cuh: fused p += t * dir, rays start at the bounding box of
-// the active cells).  A separate entry point so that the exact kernel's symbol, registers and SASS do not depend on it.
+// Tiled kernel: one thread per pixel of the grid, a warp per 4x8-pixel tile, a CTA per four tiles (16x8 pixels).
+template <int MODE, bool AOV, int MARCH>
+__device__ __forceinline__ void tiled_body(const RenderParams& P) {
+  const uint32_t tx = outside_in(blockIdx.x, gridDim.x);
+  const uint32_t trow = outside_in(blockIdx.y, gridDim.y);      // tile row among the rows this launch owns
+  const uint32_t tile_id = (blockIdx.z * gridDim.y + trow) * gridDim.x + tx;
+  if (P.prev_flag != nullptr && __ldg(P.prev_flag + tile_id) != 0u) return;  // rendered by the long-tile kernel of this launch
+  render_tile<MODE, AOV, MARCH>(P, tx, trow, blockIdx.z, tile_id);
+}
+// The tiles of the long list (one CTA each; CTAs beyond the list's length leave at once).  Launched before the main grid on a
+// high-priority stream, so that the slowest rays of the frame are the first to start.
+template <int MODE, bool AOV, int MARCH>
+__device__ __forceinline__ void long_body(const RenderParams& P) {
+  const uint32_t n = min(__ldg(P.prev_list), P.sched_cap);
+  if (blockIdx.x >= n) return;
+  const uint32_t tile_id = __ldg(P.prev_list + 1u + blockIdx.x);
+  const uint32_t per_cam = P.tiles_x * (P.tile_rows_per_band * P.own_bands);
+  const uint32_t cam_i = tile_id / per_cam, rem = tile_id - cam_i * per_cam;
+  const uint32_t trow = rem / P.tiles_x;
+  render_tile<MODE, AOV, MARCH>(P, rem - trow * P.tiles_x, trow, cam_i, tile_id);
+}
+
+template <int MODE, bool AOV>
+__global__ void __launch_bounds__(kThreads, WX_MIN_BLOCKS) raycast_kernel(const __grid_constant__ RenderParams P) {
+  tiled_body<MODE, AOV, kMarchExact>(P);
+}
+template <int MODE, bool AOV>
+__global__ void __launch_bounds__(kThreads, WX_MIN_BLOCKS) raycast_long_tiles(const __grid_constant__ RenderParams P) {
+  long_body<MODE, AOV, kMarchExact>(P);
+}
+
+// The same kernels in tolerance mode (WX_OPT_MARCH = 1, wx_device.cuh: fused p += t * dir, rays start at the bounding box of
+// the active cells).  Separate entry points so that the exact kernel's symbol, registers and SASS do not depend on them.
 template <int MODE, bool AOV>
 __global__ void __launch_bounds__(kThreads, WX_MIN_BLOCKS) raycast_kernel_tol(const __grid_constant__ RenderParams P) {
-  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t tx = outside_in(blockIdx.x, gridDim.x), trow = outside_in(blockIdx.y, gridDim.y);
-  uint32_t own_band = 0, in_band = trow;
-  if (P.tile_rows_per_band == 1u) own_band = trow, in_band = 0;
-  else if (P.own_bands > 1u) own_band = trow / P.tile_rows_per_band, in_band = trow - own_band * P.tile_rows_per_band;
-  const uint32_t band = own_band * P.shard_count + P.shard_index;
-  PixelRef q;
-  q.x = tx * kTileW + WX_LANE_X(warp, lane);
-  q.y = P.row_base + band * P.band_rows + in_band * kTileH + WX_LANE_Y(warp, lane);
-  q.cam = P.cam_base + blockIdx.z;
-  q.in_frame = q.x < P.width && q.y < P.row_end;
-  q.dispatched = q.x < P.disp_w && q.y < P.disp_h;
-  render_pixel<MODE, AOV, kMarchTolerance>(P, q);
+  tiled_body<MODE, AOV, kMarchTolerance>(P);
+}
+template <int MODE, bool AOV>
+__global__ void __launch_bounds__(kThreads, WX_MIN_BLOCKS) raycast_long_tiles_tol(const __grid_constant__ RenderParams P) {
+  long_body<MODE, AOV, kMarchTolerance>(P);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -117,7 +146,7 @@ __global__ void __launch_bounds__(kThreads, WX_MIN_BLOCKS) raycast_persistent(co
     if (tile >= P.n_chunks * 16u) break;
 #pragma unroll 1
     for (uint32_t k = 0; k < (uint32_t)WX_TILES_PER_GRAB; ++k) {
-      render_pixel<MODE, AOV>(P, pixel_of(P, tile + k, lane));
+      (void)render_pixel<MODE, AOV>(P, pixel_of(P, tile + k, lane));
       __syncwarp();
     }
   }
@@ -148,7 +177,7 @@ __global__ void __launch_bounds__(kThreads, WX_MIN_BLOCKS) raycast_persistent_ct
     chunk = __shfl_sync(0xffffffffu, chunk, 0);
     t = __shfl_sync(0xffffffffu, t, 0);
     if (chunk == kNoTile) break;
-    render_pixel<MODE, AOV>(P, pixel_of_chunk_tile(P, chunk, t, lane));
+    (void)render_pixel<MODE, AOV>(P, pixel_of_chunk_tile(P, chunk, t, lane));
     __syncwarp();
   }
 }
@@ -167,18 +196,28 @@ static cudaError_t launch_mode_persistent(const RenderParams& P, unsigned ctas, 
 
 // pad: bytes of (unused) dynamic shared memory per CTA (WX_OPT_SMEM_PAD) -- a measurement knob that lowers the number of
 // resident CTAs per SM.
+// long_stream != nullptr (and P.prev_list set): the long-tile kernel goes first, on that (high-priority) stream; the caller has
+// ordered it after `stream`'s earlier work and joins it afterwards.
 template <int MODE>
-static cudaError_t launch_mode(const RenderParams& P, dim3 grid, cudaStream_t stream, size_t pad) {
+static cudaError_t launch_mode(const RenderParams& P, dim3 grid, cudaStream_t stream, size_t pad, cudaStream_t long_stream) {
   if (pad > 48 * 1024) {
     (void)cudaFuncSetAttribute(raycast_kernel<MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pad);
     (void)cudaFuncSetAttribute(raycast_kernel<MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pad);
+  }
+  if (long_stream != nullptr && P.prev_list != nullptr) {
+    if (P.has_aov) raycast_long_tiles<MODE, true><<<P.sched_cap, kThreads, 0, long_stream>>>(P);
+    else raycast_long_tiles<MODE, false><<<P.sched_cap, kThreads, 0, long_stream>>>(P);
   }
   if (P.has_aov) raycast_kernel<MODE, true><<<grid, kThreads, pad, stream>>>(P);
   else raycast_kernel<MODE, false><<<grid, kThreads, pad, stream>>>(P);
   return cudaGetLastError();
 }
 template <int MODE>
-static cudaError_t launch_mode_tol(const RenderParams& P, dim3 grid, cudaStream_t stream) {
+static cudaError_t launch_mode_tol(const RenderParams& P, dim3 grid, cudaStream_t stream, cudaStream_t long_stream) {
+  if (long_stream != nullptr && P.prev_list != nullptr) {
+    if (P.has_aov) raycast_long_tiles_tol<MODE, true><<<P.sched_cap, kThreads, 0, long_stream>>>(P);
+    else raycast_long_tiles_tol<MODE, false><<<P.sched_cap, kThreads, 0, long_stream>>>(P);
+  }
   if (P.has_aov) raycast_kernel_tol<MODE, true><<<grid, kThreads, 0, stream>>>(P);
   else raycast_kernel_tol<MODE, false><<<grid, kThreads, 0, stream>>>(P);
   return cudaGetLastError();
@@ -191,8 +230,10 @@ static cudaError_t launch_mode_tol(const RenderParams& P, dim3 grid, cudaStream_
 // Fills the launch geometry of P (shard -> bands -> tile rows) and launches frames
 // [P.cam_base, P.cam_base + n_cams) in render mode `render_mode` (the caller groups a camera batch
 // by mode).  P.n_states is the total number of states behind P.states / P.s0.
+// sched (optional): prepares the long-tiles-first list for this launch geometry (sched->prepare fills P.prev_* / P.next_*
+// and returns the stream of the long-tile kernel, already ordered after `stream`; sched->finish joins it back).
 cudaError_t launch_raycast(RenderParams& P, uint32_t n_cams, uint32_t render_mode, cudaStream_t stream, uint32_t* launches,
-                           uint32_t* work_counter, uint32_t resident_ctas, const LaunchOptions& opt) {
+                           uint32_t* work_counter, uint32_t resident_ctas, const LaunchOptions& opt, TileSched* sched) {
   *launches = 0;
   if (P.shard_count == 0) P.shard_count = 1, P.shard_index = 0;
   if (P.row_end == 0 || P.row_end > P.height) P.row_end = P.height;
@@ -241,21 +282,34 @@ cudaError_t launch_raycast(RenderParams& P, uint32_t n_cams, uint32_t render_mod
   }
   dim3 grid(P.tiles_x, (unsigned)tile_rows, n_cams);
   *launches = 1;
+  cudaStream_t long_stream = nullptr;
+  const uint64_t n_tiles = (uint64_t)P.tiles_x * tile_rows * n_cams;
+  // (modes 3 and 4 spend most of their time in secondary rays, which the primary ray's iteration count does not predict:
+  // measured no gain there, profiles/r2_longfirst.txt)
+  if (sched != nullptr && opt.long_first && render_mode <= 2u && n_tiles >= 512 && n_tiles < (1ull << 31)) {
+    cudaError_t e = sched->prepare(P, n_cams, (uint32_t)n_tiles, stream, &long_stream);
+    if (e != cudaSuccess) return e;
+    if (long_stream != nullptr) *launches = 2;
+  }
+  cudaError_t le;
   if (opt.march == kMarchTolerance && render_mode != 2u) {  // mode 2 colours the iteration count: always exact
     switch (render_mode) {
-      case 1: return launch_mode_tol<1>(P, grid, stream);
-      case 3: return launch_mode_tol<3>(P, grid, stream);
-      case 4: return launch_mode_tol<4>(P, grid, stream);
-      default: return launch_mode_tol<0>(P, grid, stream);
+      case 1: le = launch_mode_tol<1>(P, grid, stream, long_stream); break;
+      case 3: le = launch_mode_tol<3>(P, grid, stream, long_stream); break;
+      case 4: le = launch_mode_tol<4>(P, grid, stream, long_stream); break;
+      default: le = launch_mode_tol<0>(P, grid, stream, long_stream); break;
+    }
+  } else {
+    switch (render_mode) {
+      case 1: le = launch_mode<1>(P, grid, stream, opt.smem_pad, long_stream); break;
+      case 2: le = launch_mode<2>(P, grid, stream, opt.smem_pad, long_stream); break;
+      case 3: le = launch_mode<3>(P, grid, stream, opt.smem_pad, long_stream); break;
+      case 4: le = launch_mode<4>(P, grid, stream, opt.smem_pad, long_stream); break;
+      default: le = launch_mode<0>(P, grid, stream, opt.smem_pad, long_stream); break;  // Gray and the shader's `default:` arms
     }
   }
-  switch (render_mode) {
-    case 1: return launch_mode<1>(P, grid, stream, opt.smem_pad);
-    case 2: return launch_mode<2>(P, grid, stream, opt.smem_pad);
-    case 3: return launch_mode<3>(P, grid, stream, opt.smem_pad);
-    case 4: return launch_mode<4>(P, grid, stream, opt.smem_pad);
-    default: return launch_mode<0>(P, grid, stream, opt.smem_pad);  // Gray and the shader's `default:` arms
-  }
+  if (le == cudaSuccess && long_stream != nullptr) le = sched->finish(stream);
+  return le;
 }
 
 }  // namespace wx
