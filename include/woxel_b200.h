@@ -229,9 +229,10 @@ typedef enum WxOption {
   WX_OPT_RENDER_CHUNKS = 3, /* row chunks of a pipelined wx_render (0 = automatic) */
   WX_OPT_SMEM_PAD = 4,      /* bytes of unused dynamic shared memory per CTA (lowers the resident CTAs per SM; measurement only) */
   WX_OPT_NVTX = 5,          /* 1: NVTX ranges around upload / sweep / render / read-back (default 0) */
-  WX_OPT_LONG_FIRST = 6     /* 1 (default): the tiles that held the longest rays in the previous launch of the same frame geometry
+  WX_OPT_LONG_FIRST = 6,    /* 1 (default): the tiles that held the longest rays in the previous launch of the same frame geometry
                                start first (a small high-priority kernel ahead of the main grid): shortens the drain at the end of
                                a launch.  Same pixels; 0 = plain launches */
+  WX_OPT_LONG_THRESHOLD = 7 /* iterations of a primary ray from which its tile counts as long (default 96) */
 } WxOption;
 int wx_set_option(WxContext *ctx, int option, int64_t value);
 int wx_get_option(const WxContext *ctx, int option, int64_t *value_out);

@@ -26,6 +26,7 @@ pub const WX_OPT_RENDER_CHUNKS: c_int = 3;
 pub const WX_OPT_SMEM_PAD: c_int = 4;
 pub const WX_OPT_NVTX: c_int = 5;
 pub const WX_OPT_LONG_FIRST: c_int = 6;
+pub const WX_OPT_LONG_THRESHOLD: c_int = 7;
 
 #[repr(C)]
 pub struct WxContext {

@@ -19,6 +19,8 @@ def apply_env(ctx):
         ctx.set_option(_ffi.WX_OPT_MARCH, 1)
     if os.environ.get("WX_LONG_FIRST") in ("0", "1"):
         ctx.set_option(_ffi.WX_OPT_LONG_FIRST, int(os.environ["WX_LONG_FIRST"]))
+    if os.environ.get("WX_LONG_THRESHOLD"):
+        ctx.set_option(_ffi.WX_OPT_LONG_THRESHOLD, int(os.environ["WX_LONG_THRESHOLD"]))
     if os.environ.get("WX_NVTX") == "1":
         ctx.set_option(_ffi.WX_OPT_NVTX, 1)
     return ctx

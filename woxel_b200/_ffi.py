@@ -106,7 +106,7 @@ CUDA_API = {
     "wx_get_option": (C.c_int, [vp, C.c_int, C.POINTER(C.c_int64)]),
 }
 # WxOption (include/woxel_b200.h)
-WX_OPT_MARCH, WX_OPT_KERNEL, WX_OPT_RENDER_CHUNKS, WX_OPT_SMEM_PAD, WX_OPT_NVTX, WX_OPT_LONG_FIRST = 1, 2, 3, 4, 5, 6
+WX_OPT_MARCH, WX_OPT_KERNEL, WX_OPT_RENDER_CHUNKS, WX_OPT_SMEM_PAD, WX_OPT_NVTX, WX_OPT_LONG_FIRST, WX_OPT_LONG_THRESHOLD = 1, 2, 3, 4, 5, 6, 7
 f3, u3, i3 = C.POINTER(C.c_float), C.POINTER(C.c_uint32), C.POINTER(C.c_int32)
 HOST_API = {
     "wxh_last_error": (C.c_char_p, []),

@@ -97,7 +97,7 @@ struct SchedEntry final : TileSched {
     if (e == cudaSuccess) e = cudaMemsetAsync(list[nxt], 0, 4, stream);
     if (e != cudaSuccess) return e;
     P.next_list = list[nxt], P.next_flag = flag[nxt];
-    P.sched_cap = cap, P.sched_threshold = 96u;  // ~3x the mean primary ray of the benchmark scenes (20-50 iterations)
+    P.sched_cap = cap;  // (P.sched_threshold: the launcher's option)
     P.prev_list = nullptr, P.prev_flag = nullptr;
     if (valid) {
       P.prev_list = list[cur], P.prev_flag = flag[cur];
@@ -1209,6 +1209,10 @@ extern "C" int wx_set_option(WxContext* ctx, int option, int64_t value) {
       if (value != 0 && value != 1) break;
       ctx->opt.long_first = (int)value;
       return WX_OK;
+    case WX_OPT_LONG_THRESHOLD:
+      if (value < 1 || value > 1000) break;
+      ctx->opt.long_threshold = (uint32_t)value;
+      return WX_OK;
     default:
       return fail(ctx, WX_ERR_INVALID_ARGUMENT, "wx_set_option: unknown option");
   }
@@ -1224,6 +1228,7 @@ extern "C" int wx_get_option(const WxContext* ctx, int option, int64_t* value_ou
     case WX_OPT_SMEM_PAD: *value_out = (int64_t)ctx->opt.smem_pad; return WX_OK;
     case WX_OPT_NVTX: *value_out = ctx->nvtx ? 1 : 0; return WX_OK;
     case WX_OPT_LONG_FIRST: *value_out = ctx->opt.long_first; return WX_OK;
+    case WX_OPT_LONG_THRESHOLD: *value_out = ctx->opt.long_threshold; return WX_OK;
     default: return WX_ERR_INVALID_ARGUMENT;
   }
 }

@@ -19,6 +19,7 @@ struct LaunchOptions {
   size_t smem_pad = 0;   // WX_OPT_SMEM_PAD
   int march = 0;         // WX_OPT_MARCH: 0 exact, 1 tolerance mode
   int long_first = 1;    // WX_OPT_LONG_FIRST: tiles that held long rays in the previous launch of the same geometry start first
+  uint32_t long_threshold = 96;  // WX_OPT_LONG_THRESHOLD: ~3x the mean primary ray of the benchmark scenes (20-50 iterations)
 };
 
 // Long-tiles-first state of one launch geometry on one stream (wx_api.cu owns the objects; wx_raycast.cu drives them).

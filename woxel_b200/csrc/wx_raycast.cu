@@ -287,6 +287,7 @@ cudaError_t launch_raycast(RenderParams& P, uint32_t n_cams, uint32_t render_mod
   // (modes 3 and 4 spend most of their time in secondary rays, which the primary ray's iteration count does not predict:
   // measured no gain there, profiles/r2_longfirst.txt)
   if (sched != nullptr && opt.long_first && render_mode <= 2u && n_tiles >= 512 && n_tiles < (1ull << 31)) {
+    P.sched_threshold = opt.long_threshold;
     cudaError_t e = sched->prepare(P, n_cams, (uint32_t)n_tiles, stream, &long_stream);
     if (e != cudaSuccess) return e;
     if (long_stream != nullptr) *launches = 2;
