@@ -33,7 +33,12 @@ for _ in range(a.frames):
     ctx.render_device(tree, st, bench.WIDTH, bench.HEIGHT, buf.value)
     ctx.check(lib.wx_stream_synchronize(ctx._h, 0, None))
     ms.append(ctx.last_render_info().kernel_ms)
+import numpy as np  # noqa: E402
+frame = np.zeros((bench.HEIGHT, bench.WIDTH), np.uint32)
+ctx.check(lib.wx_memcpy_d2h(ctx._h, 0, frame.ctypes.data, buf, frame.nbytes, None))
+ctx.check(lib.wx_stream_synchronize(ctx._h, 0, None))
+checksum = int(frame.sum(dtype=np.uint64))  # equal checksums of two builds on the same scene/mode = (almost surely) equal frames
 rays = (bench.WIDTH // 8 * 8) * (bench.HEIGHT // 4 * 4)
 best = sorted(ms[1:])[len(ms[1:]) // 2] if len(ms) > 1 else ms[0]
 print("lib", os.environ.get("WOXEL_B200_LIB", "default"), "scene", a.scene, "mode", a.mode, "median_ms", round(best, 4),
-      "Mrays/s", round(rays / best / 1e3, 1), "all_ms", [round(m, 3) for m in ms])
+      "Mrays/s", round(rays / best / 1e3, 1), "checksum", checksum, "all_ms", [round(m, 3) for m in ms])

@@ -414,6 +414,9 @@ constexpr uint32_t kMaxRaySteps = 1000u;
 #ifndef WX_EMU_STEP
 #define WX_EMU_STEP(dv0, dbits) ((void)(dv0))  // tests/emu records the level walk of every step here; nothing on the device
 #endif
+#ifndef WX_STAGE_MIN
+#define WX_STAGE_MIN 8  // lanes that must share a leaf before its brick is staged (WX_STAGE_LEAF experiment)
+#endif
 #ifndef WX_UNROLL
 #define WX_UNROLL 2  // two steps per loop trip: the cursor's last-voxel registers alternate instead of being copied
 #endif
@@ -692,6 +695,9 @@ struct GridRay {
   uint32_t dbits;            // 0: w4 and w3 valid (last lookup ended in a leaf), 8: w4 valid, 128: neither
   uint32_t w4, w3;           // index bases of the N4 table / leaf brick the cursor is in (grid_word4 << 4 / grid_word3 << 3)
   uint32_t i;
+#if defined(WX_STAGE_LEAF) && !defined(WX_HOST_EMU)
+  uint32_t stage_tag, stage_phase;  // A/B experiment: brick in this warp's shared-memory slot; parity of its mbarrier (2 = not initialised)
+#endif
 
   __device__ __forceinline__ void init(V3 src, V3 dir, V3 idir) {
     pxy = pk(src.x, src.y), pz = src.z;
@@ -704,6 +710,9 @@ struct GridRay {
     size = 1.f;
     dbits = 128u, w4 = 0u, w3 = 0u;
     i = 0;
+#if defined(WX_STAGE_LEAF) && !defined(WX_HOST_EMU)
+    stage_tag = 0xfffffffeu, stage_phase = 2u;
+#endif
   }
 
   // One iteration of hdda_ray's loop body (:90-122) without the counter: `last` is the voxel of the lookup before, `cur`
@@ -730,10 +739,67 @@ struct GridRay {
       if ((int32_t)e >= 0) dbits = 8u, size = __uint_as_float(e), lvl = 0u;
       else w3 = e << 3, lvl = 3u;
     }
+#if defined(WX_STAGE_LEAF) && !defined(WX_HOST_EMU)
+    // A/B EXPERIMENT (never the default; VERDICT r1 item 6, north_star "leaf bricks staged in shared memory, TMA where the layout
+    // allows"): when at least WX_STAGE_MIN lanes of the warp are about to read the same leaf, its 512-byte brick is copied into a
+    // per-warp slot of shared memory -- WX_STAGE_LEAF=1: cooperatively with 16-byte loads (LDG.128 + STS.128), =2: one
+    // cp.async.bulk (TMA, UBLKCP) completing on an mbarrier -- and those lanes read their voxel from there; the slot stays valid
+    // while the warp keeps returning to that leaf.  The decision is taken where all lanes still marching are converged (after
+    // the per-level walk), so the slot is only ever touched by all live lanes together.  Results are unchanged.
+    {
+      __shared__ __align__(128) uint8_t s_brick[8][512];
+      __shared__ __align__(8) unsigned long long s_bar[8];
+      const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+      const bool leaf = lvl == 3u;
+      const uint32_t brick = leaf ? w3 + ((x & ~7u) * 64u + (y & ~7u) * 8u + (z & ~7u)) : 0xffffffffu;  // byte offset of the leaf's brick
+      const uint32_t live = __activemask();
+      const uint32_t want = __ballot_sync(live, leaf);
+      if (want != 0u) {
+        const uint32_t lead_brick = __shfl_sync(live, brick, __ffs(want) - 1);
+        const uint32_t same = __ballot_sync(live, brick == lead_brick);
+        if (stage_tag != lead_brick && __popc(same) >= WX_STAGE_MIN) {
+#if WX_STAGE_LEAF == 1
+          const uint32_t rank = __popc(live & ((1u << lane) - 1u)), n = __popc(live);
+          for (uint32_t k = rank; k < 32u; k += n)
+            reinterpret_cast<uint4*>(s_brick[warp])[k] = __ldg(reinterpret_cast<const uint4*>(T.l3 + lead_brick) + k);
+#else
+          const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s_bar[warp]), dst = (uint32_t)__cvta_generic_to_shared(s_brick[warp]);
+          if (stage_phase == 2u) {  // first use by this warp: initialise its barrier
+            if (lane == (uint32_t)(__ffs(live) - 1)) {
+              asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+              asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            }
+            stage_phase = 0u;
+            __syncwarp(live);
+          }
+          if (lane == (uint32_t)(__ffs(live) - 1)) {
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], 512;" ::"r"(bar) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], 512, [%2];" ::"r"(dst),
+                         "l"(T.l3 + lead_brick), "r"(bar)
+                         : "memory");
+          }
+          uint32_t done = 0u;
+          while (!done)
+            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(bar), "r"(stage_phase) : "memory");
+          stage_phase ^= 1u;
+#endif
+          stage_tag = lead_brick;
+          __syncwarp(live);
+        }
+        if (leaf) {
+          dbits = 0u;
+          if (brick == stage_tag) size = u32_to_float(s_brick[warp][((x & 7u) << 6) | ((y & 7u) << 3) | (z & 7u)]);
+          else size = u32_to_float(__ldg(T.l3 + (uint32_t)(x * 64u + y * 8u + z + w3)));
+        }
+        __syncwarp(live);  // nobody restages while a lane still reads
+      }
+    }
+#else
     if (lvl == 3u) {
       dbits = 0u;
       size = u32_to_float(__ldg(T.l3 + (uint32_t)(x * 64u + y * 8u + z + w3)));
     }
+#endif
     if (size == 0.f || size >= 1.f) WX_EMU_STEP(dv >= 128u ? 128u : dv, dbits);  // (tests/emu only; a slow cell's lookup is redone, and traced, by march_fast)
     if (size < 1.f) return true;  // hit, or a slow cell
     const float r = rcp_approx(size);
