@@ -200,3 +200,26 @@ def test_crafted_blosc_header_is_rejected_before_any_allocation():
         with pytest.raises(W.vdb.VdbError):
             W.vdb.blosc_decompress(frame2[:4] + (1 << 20).to_bytes(4, "little") + (0xFFFFFFF0).to_bytes(4, "little") + frame2[12:])
         assert time.perf_counter() - t0 < 0.5
+
+
+def test_blosc_frames_with_streams_from_the_real_codec_libraries():
+    """tests/golden/blosc_frames.npz (tests/golden/make_blosc_golden.py): frames whose compressed streams were produced by liblz4,
+    libsnappy (both through pyarrow) and zlib -- not by this repository's own encoders -- in every shuffle / block-size
+    combination.  The product decoder must return the payloads byte for byte.  (The frame CONTAINER is still written by
+    tests/vdb_writer.py: c-blosc itself is not available in this image.)"""
+    import os
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "blosc_frames.npz"))
+    frames = [k for k in z.files if k.startswith("frame/")]
+    assert len(frames) >= 70
+    seen = set()
+    for k in frames:
+        _, pname, codec, shuffle, _ = k.split("/")
+        assert W.vdb.blosc_decompress(z[k].tobytes()) == z[f"payload/{pname}"].tobytes(), k
+        seen.add((codec, shuffle))
+    assert seen >= {(c, s) for c in ("lz4", "snappy", "zlib") for s in ("none", "byte", "bit")}
+    # a real-library stream cut short or with a flipped byte is an error, never a crash or a wrong size
+    k = "frame/sdf_f32/lz4/byte/0"
+    good = bytearray(z[k].tobytes())
+    for cut in (len(good) - 1, len(good) // 2, 40):
+        with pytest.raises(W.vdb.VdbError):
+            W.vdb.blosc_decompress(bytes(good[:cut]))

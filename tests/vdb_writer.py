@@ -144,11 +144,11 @@ def shuffle(data: bytes, typesize: int) -> bytes:
     return head.tobytes() + a[n * typesize:].tobytes()
 
 
-BLOSC_CODECS = {"blosclz": 0, "lz4": 1, "zlib": 3}
+BLOSC_CODECS = {"blosclz": 0, "lz4": 1, "snappy": 2, "zlib": 3}
 
 
 def blosc_compress(data: bytes, typesize: int, do_shuffle: bool = True, blocksize: int | None = None, force_memcpy: bool = False,
-                   codec: str = "lz4", bit_shuffle: bool = False) -> bytes:
+                   codec: str = "lz4", bit_shuffle: bool = False, encode=None) -> bytes:
     """A c-blosc 1.x frame with the LZ4 codec.  header: version 2, versionlz 1, flags (bit0 shuffle, bit1 memcpyed,
     bits 5-7 = 1: LZ4), typesize, nbytes, blocksize, cbytes; then int32 block offsets; a block is split into `typesize`
     streams when typesize <= 16 and blocksize / typesize >= 128 (never the leftover block); every stream is an int32
@@ -159,7 +159,10 @@ def blosc_compress(data: bytes, typesize: int, do_shuffle: bool = True, blocksiz
     split = typesize <= 16 and blocksize // typesize >= 128
     byte_sh = do_shuffle and typesize > 1 and not bit_shuffle
     flags = (1 if byte_sh else 0) | (4 if bit_shuffle else 0) | (0 if split else 0x10) | (BLOSC_CODECS[codec] << 5)
-    encode = {"lz4": lz4_compress_block, "blosclz": blosclz_compress_block, "zlib": lambda b: zlib.compress(b, 6)}[codec]
+    # `encode`: the stream compressor; by default this module's own encoders -- tests/golden/make_blosc_golden.py passes the REAL
+    # libraries' (liblz4 / libsnappy through pyarrow, zlib) so that the decoders are also checked against streams they did not write
+    if encode is None:
+        encode = {"lz4": lz4_compress_block, "blosclz": blosclz_compress_block, "zlib": lambda b: zlib.compress(b, 6)}[codec]
     if force_memcpy or nbytes < 128:
         flags |= 2
         return struct.pack("<BBBBIII", 2, 1, flags, typesize, nbytes, blocksize, 16 + nbytes) + data

@@ -246,6 +246,60 @@ void bit_unshuffle_block(const uint8_t* in, uint8_t* out, size_t bsize, size_t t
   memcpy(out + ne8 * typesize, in + ne8 * typesize, bsize - ne8 * typesize);
 }
 
+// Snappy raw format (c-blosc codec 2; google/snappy format_description.txt): a varint with the uncompressed length, then
+// elements -- tag & 3 == 0: a literal run ((tag >> 2) + 1 bytes; 60..63 in the upper bits mean the length - 1 follows in 1..4
+// little-endian bytes); 1: a copy of ((tag >> 2) & 7) + 4 bytes from an 11-bit offset (3 bits in the tag, 8 in the next byte);
+// 2 / 3: a copy of (tag >> 2) + 1 bytes from a 16- / 32-bit little-endian offset.  Copies may overlap their own output.
+static bool snappy_decompress_block(const uint8_t* src, size_t n, uint8_t* dst, size_t dst_len) {
+  size_t ip = 0, op = 0;
+  uint64_t ulen = 0;
+  for (int shift = 0;; shift += 7) {
+    if (ip >= n || shift > 35) return false;
+    const uint8_t b = src[ip++];
+    ulen |= (uint64_t)(b & 0x7f) << shift;
+    if (!(b & 0x80)) break;
+  }
+  if (ulen != dst_len) return false;
+  while (ip < n) {
+    const uint8_t tag = src[ip++];
+    size_t len, off;
+    if ((tag & 3) == 0) {
+      len = (size_t)(tag >> 2) + 1;
+      if (len > 60) {
+        const size_t extra = len - 60;
+        if (ip + extra > n) return false;
+        len = 0;
+        for (size_t k = 0; k < extra; ++k) len |= (size_t)src[ip + k] << (8 * k);
+        len += 1;
+        ip += extra;
+      }
+      if (len > n - ip || len > dst_len - op) return false;
+      memcpy(dst + op, src + ip, len);
+      ip += len, op += len;
+      continue;
+    }
+    if ((tag & 3) == 1) {
+      if (ip >= n) return false;
+      len = (size_t)((tag >> 2) & 7) + 4;
+      off = ((size_t)(tag >> 5) << 8) | src[ip++];
+    } else if ((tag & 3) == 2) {
+      if (ip + 2 > n) return false;
+      len = (size_t)(tag >> 2) + 1;
+      off = (size_t)src[ip] | ((size_t)src[ip + 1] << 8);
+      ip += 2;
+    } else {
+      if (ip + 4 > n) return false;
+      len = (size_t)(tag >> 2) + 1;
+      off = (size_t)src[ip] | ((size_t)src[ip + 1] << 8) | ((size_t)src[ip + 2] << 16) | ((size_t)src[ip + 3] << 24);
+      ip += 4;
+    }
+    if (off == 0 || off > op || len > dst_len - op) return false;
+    for (size_t k = 0; k < len; ++k) dst[op + k] = dst[op + k - off];  // byte by byte: the copy may overlap what it writes
+    op += len;
+  }
+  return op == dst_len;
+}
+
 // expected: the size the caller knows the frame must decode to (count * element size), or kAnySize.  Checked BEFORE anything is
 // allocated: the header of a crafted 16-byte frame may claim 4 GiB.  max_bytes: the most the caller has room for.
 constexpr size_t kAnySize = (size_t)-1;
@@ -269,8 +323,8 @@ std::vector<uint8_t> blosc_decompress(const uint8_t* f, size_t n, size_t expecte
     return out;
   }
   const int codec = flags >> 5;
-  if (codec != 0 && codec != 1 && codec != 3)
-    throw VdbError(VdbError::UnsupportedBloscFormat, "Blosc codec " + std::to_string(codec) + " is not supported (BloscLZ, LZ4 and zlib are)");
+  if (codec != 0 && codec != 1 && codec != 2 && codec != 3)
+    throw VdbError(VdbError::UnsupportedBloscFormat, "Blosc codec " + std::to_string(codec) + " is not supported (BloscLZ, LZ4, Snappy and zlib are; Zstd is not)");
   const bool byte_shuffled = (flags & 0x1) && typesize > 1, bit_shuffled = !byte_shuffled && (flags & 0x4) && blocksize >= typesize;
   if (blocksize == 0) throw bad("zero block size");
   const size_t nblocks = (nbytes + blocksize - 1) / blocksize;
@@ -296,6 +350,8 @@ std::vector<uint8_t> blosc_decompress(const uint8_t* f, size_t n, size_t expecte
         if (!lz4_decompress_block(f + at, cb, d, neblock)) throw bad("corrupt LZ4 stream");
       } else if (codec == 0) {
         if (!blosclz_decompress_block(f + at, cb, d, neblock)) throw bad("corrupt BloscLZ stream");
+      } else if (codec == 2) {
+        if (!snappy_decompress_block(f + at, cb, d, neblock)) throw bad("corrupt Snappy stream");
       } else {
         uLongf dlen = (uLongf)neblock;
         if (uncompress(d, &dlen, f + at, (uLong)cb) != Z_OK || dlen != neblock) throw bad("corrupt zlib stream");
