@@ -676,6 +676,23 @@ struct VoxelId {
   uint32_t x, y, z;  // biased voxel coordinates
 };
 
+// Warp votes of march_grid's top-level runs.  They only ever select between code paths that give each lane the same result;
+// tests/emu runs the lanes one by one (a "warp" of one lane).
+__device__ __forceinline__ uint32_t warp_live() {  // the lanes executing this together with the caller
+#ifndef WX_HOST_EMU
+  return __activemask();
+#else
+  return 1u;
+#endif
+}
+__device__ __forceinline__ bool warp_all(uint32_t live, bool p) {  // p holds on every lane of `live` (all of them must be here)
+#ifndef WX_HOST_EMU
+  return __all_sync(live, p) != 0;
+#else
+  return p;
+#endif
+}
+
 __device__ __forceinline__ VoxelId opaque_copy(const VoxelId& s) {
   VoxelId d;
 #ifndef WX_HOST_EMU
@@ -802,6 +819,13 @@ struct GridRay {
 #endif
     if (size == 0.f || size >= 1.f) WX_EMU_STEP(dv >= 128u ? 128u : dv, dbits);  // (tests/emu only; a slow cell's lookup is redone, and traced, by march_fast)
     if (size < 1.f) return true;  // hit, or a slow cell
+    advance<TOL>(txy, tz);
+    return false;
+  }
+
+  // The step itself (:104-121) from the position whose floor is (txy, tz) (kMagic-biased) through a cell of pitch `size`.
+  template <bool TOL>
+  __device__ __forceinline__ void advance(const f32x2 txy, const float tz) {
     const float r = rcp_approx(size);
     const float hr = 0.5f * r;
     const f32x2 xfxy = add2(txy, bc(-kMagic));                         // float(floor(p)), exact
@@ -830,7 +854,48 @@ struct GridRay {
     if (lty == lt) py += ndy;
     if (ltz == lt) pz += ndz;
     pxy = pk(px, py);
-    return false;
+  }
+
+  // A run of top-level steps (march_grid): while EVERY lane of `live` (the lanes that entered together) finds a plain tile in
+  // the world grid -- size >= 128, i.e. every top-level tile that is not active -- all of them step, with no cursor test, no
+  // level dispatch and no divergence inside the loop.  The first lookup that is something else for some lane ends the run for
+  // everybody; each lane then finishes ITS lookup of that round: a plain tile is stepped through; a child leaves the cursor
+  // saying "inside that N4, at this voxel" (`pending`, dbits = 8), so that the generic step continues the lookup from the N4
+  // table; a hit or a slow cell ends the march (returns true, i not counted, as in step()).  `limit`: a lane only steps here
+  // while i < limit.
+  template <bool TOL>
+  __device__ __forceinline__ bool top_run(const DevTree& T, VoxelId& pending, uint32_t live, uint32_t limit) {
+    for (;;) {
+      const f32x2 txy = add2_rd(pxy, bc(kMagic));
+      const float tz = __fadd_rd(pz, kMagic);
+      const uint32_t x = (uint32_t)txy, y = (uint32_t)(txy >> 32), z = __float_as_uint(tz);
+      const uint32_t e = __ldg(T.grid + (uint32_t)((x >> 7) * kGS2 + (y >> 7) * kGS + (z >> 7) + kGridK));
+      const bool plain = (int32_t)e >= 0x43000000 && i < limit;  // positive floats order like ints
+      if (warp_all(live, plain)) {
+        size = __uint_as_float(e);
+        WX_EMU_STEP(128u, 128u);
+        advance<TOL>(txy, tz);
+        i += 1u;
+        continue;
+      }
+      // the run is over; this lane's own lookup:
+      if (plain) {
+        size = __uint_as_float(e);
+        WX_EMU_STEP(128u, 128u);
+        advance<TOL>(txy, tz);
+        i += 1u;
+        return false;
+      }
+      if ((int32_t)e >= 0x43000000) return false;  // out of budget for this loop: the generic steps take over (and redo the lookup)
+      if ((int32_t)e >= 0) {  // 0.0f = active tile (hit), kEntryVoid / kEntrySlow
+        size = __uint_as_float(e);
+        if (e == 0u) WX_EMU_STEP(128u, 128u);
+        return true;
+      }
+      w4 = e << 4, dbits = 8u;
+      pending.x = x, pending.y = y, pending.z = z;
+      return false;
+    }
   }
 };
 
@@ -854,25 +919,44 @@ template <bool TOL>
 __device__ __forceinline__ HitOut march_grid(const DevTree& T, V3 src, V3 dir, V3 idir) {
   GridRay r;
   r.init(TOL ? clip_to_bbox(T, src, dir, idir) : src, dir, idir);
-  // Two steps per trip over two alternating VoxelIds: nothing is copied inside the loop, and the step budget (kMaxRaySteps
-  // is even) is tested once per trip.  The copies at the exits are opaque so that the compiler does not merge a and b.
-  VoxelId a{0u, 0u, 0u}, b{0u, 0u, 0u}, v;
-  for (;;) {
+  // Two steps per trip over two alternating VoxelIds: nothing is copied inside the loop, and the step budget is tested once
+  // per trip.  The copies at the exits are opaque so that the compiler does not merge a and b.
+  // Top-level runs (-DWX_TOP_RUN, an A/B variant that is NOT the default): 40 % of the warp steps of the bench frame read the
+  // world grid only (rays crossing empty tiles), and after such a step the next lookup starts at the grid again.  While that
+  // holds for every lane of the warp still marching, the lanes can run top_run(), a loop of their own without cursor test,
+  // level dispatch and convergence barriers (45 instead of 53 instructions per step); a lane that meets a child there hands
+  // its lookup to the generic step below, so lanes may leave a run with different iteration counts (hence the single last
+  // step after the loop).  Measured: the warp vote that decides whether to enter a run costs 8 instructions per trip of the
+  // generic loop (VOTE.ANY + R2UR + BRA.DIV + VOTE.ALL + ...), which eats the gain: 0.756 ms with runs, 0.740 ms without.
+  VoxelId a{0u, 0u, 0u}, b{0u, 0u, 0u}, v{0u, 0u, 0u};
+  bool ended = false;
+  while (r.i < kMaxRaySteps - 1u) {  // two lookups or more to go
+#ifdef WX_TOP_RUN  // A/B: measured 2 % SLOWER than without (profiles/r2_top_run_ab.txt) -- not the default
+    const uint32_t live = warp_live();
+    if (warp_all(live, r.dbits == 128u && r.i < kMaxRaySteps - 2u) && r.template top_run<TOL>(T, a, live, kMaxRaySteps - 2u)) {
+      ended = true;  // (the voxel is not needed for an end on the top level)
+      break;
+    }
+#endif
     if (r.template step<TOL>(T, a, b)) {
-      v = opaque_copy(b);
+      v = opaque_copy(b), ended = true;
       break;
     }
     if (r.template step<TOL>(T, b, a)) {
-      v = opaque_copy(a), r.i += 1u;
+      v = opaque_copy(a), r.i += 1u, ended = true;
       break;
     }
     r.i += 2u;
-    if (r.i >= kMaxRaySteps) {
-      v = opaque_copy(a);
-      break;
+  }
+  if (!ended) {
+    if (r.i == kMaxRaySteps - 1u) {  // one lookup left (the count became odd in a top-level run)
+      if (r.template step<TOL>(T, a, b)) ended = true;
+      else r.i += 1u;
+      v = opaque_copy(b);
+    } else {
+      v = opaque_copy(a);  // out of steps: the voxel of the last lookup
     }
   }
-  const bool ended = r.i < kMaxRaySteps;
   const V3 p = V3{lo(r.pxy), hi(r.pxy), r.pz};
   HitOut out;
   out.p = p;
