@@ -328,6 +328,7 @@ def main():
 
     step_ms = []          # device time of every timed step of this rank
     launches = [0]
+    launches_per_call = [1]
 
     def step(timed_events=None):
         flush.fill_(1)  # evict L2 (126 MB) between steps; outside the timed region
@@ -344,7 +345,7 @@ def main():
         ctx.render_device(tree, state, WIDTH, HEIGHT, my_frame, stream=stream.cuda_stream)
         if timed_events is not None:
             timed_events[1].record(stream)
-            launches[0] += 1
+            launches[0] += launches_per_call[0]  # 1, or 2 with the long-tile kernel (read once after the warm-up, below)
 
     def timed_run(n_warm, n_steps):
         """n_warm untimed + n_steps timed steps between barrier + synchronize brackets.  Returns (ms per step = MAX over ranks of
@@ -376,6 +377,8 @@ def main():
     for _ in range(args.warmup):
         step()
     sync_all()
+    if gather != "dma":
+        launches_per_call[0] = int(ctx.last_render_info().launches)  # kernels one wx_render_device call launches in steady state
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
