@@ -61,7 +61,7 @@ struct SchedEntry final : TileSched {
       if (flag[k]) (void)cudaFree(flag[k]);
       list[k] = flag[k] = nullptr;
     }
-    n_tiles = cap = 0, valid = false;
+    n_tiles = cap = 0, valid = false, prepared = false;
   }
   ~SchedEntry() override {
     release();
@@ -98,6 +98,7 @@ struct SchedEntry final : TileSched {
     if (e != cudaSuccess) return e;
     P.next_list = list[nxt], P.next_flag = flag[nxt];
     P.sched_cap = cap;  // (P.sched_threshold: the launcher's option)
+    prepared = true;
     P.prev_list = nullptr, P.prev_flag = nullptr;
     if (valid) {
       P.prev_list = list[cur], P.prev_flag = flag[cur];
@@ -108,12 +109,19 @@ struct SchedEntry final : TileSched {
     }
     return cudaSuccess;
   }
+  void attach(RenderParams& P) override {
+    P.prev_list = nullptr, P.prev_flag = nullptr, P.next_list = nullptr, P.next_flag = nullptr;
+    if (!prepared) return;
+    P.next_list = list[cur ^ 1], P.next_flag = flag[cur ^ 1], P.sched_cap = cap;
+    if (valid) P.prev_list = list[cur], P.prev_flag = flag[cur];
+  }
   cudaError_t finish(cudaStream_t stream) override {
     cudaError_t e = cudaEventRecord(join, ls);
     if (e == cudaSuccess) e = cudaStreamWaitEvent(stream, join, 0);
     return e;
   }
-  void launched() { cur ^= 1, valid = true; }  // the set just recorded becomes "previous"
+  void launched() { cur ^= 1, valid = true, prepared = false; }  // the set just recorded becomes "previous"
+  bool prepared = false;  // prepare() has run for the frame being launched
 };
 constexpr size_t kSchedEntries = 24;
 
@@ -694,10 +702,12 @@ extern "C" int wx_tree_info(const WxTree* tree, WxTreeInfo* info) {
 // Frames [cam0, cam0 + ncam) of `states`, rows [row0, row1) (row1 == 0: all rows; with a shard row0 must be a multiple of
 // one round of the band deal, shard->count * shard->band_rows).
 // `states_on_device`: the whole batch is already in s.d_states (a pipelined wx_render uploads it once).
+static SchedEntry* find_sched(DeviceSlot& s, const SchedKey& key);
 static int launch_on(WxContext* ctx, int dev_i, const WxTree* tree, const WxState* states, uint32_t n_states, uint32_t width,
                      uint32_t height, uint8_t* rgba_dev, const WxAov* aov_dev, const WxShard* shard, cudaStream_t stream,
                      uint32_t* launches_out, uint32_t cam0 = 0, uint32_t ncam = 0xffffffffu, uint32_t row0 = 0, uint32_t row1 = 0,
-                     bool states_on_device = false, bool long_first = true) {
+                     bool states_on_device = false, bool long_first = true, SchedEntry* frame_sched = nullptr,
+                     const SchedCall* sched_call = nullptr) {
   DeviceSlot& s = ctx->dev[dev_i];
   const TreeOnDevice& o = tree->on[dev_i];
   WxState* launch_states = nullptr;
@@ -744,30 +754,17 @@ static int launch_on(WxContext* ctx, int dev_i, const WxTree* tree, const WxStat
     uint32_t l = 0;
     uint32_t* counter = s.counters + (s.counter_next++ % kCounterRing);
     // long-tiles-first state of this launch geometry on this stream (plain launches when the option is off)
-    SchedEntry* se = nullptr;
+    SchedEntry* se = frame_sched;
     P.prev_list = nullptr, P.prev_flag = nullptr, P.next_list = nullptr, P.next_flag = nullptr;
-    if (long_first && ctx->opt.long_first && ctx->opt.kernel == 0) {
+    if (!se && long_first && ctx->opt.long_first && ctx->opt.kernel == 0) {
       SchedKey key;
       memset(&key, 0, sizeof(key));
       key.tree = tree, key.stream = stream, key.width = width, key.height = height, key.cam0 = b, key.ncam = e - b;
       key.shard_index = P.shard_index, key.shard_count = P.shard_count, key.band_rows = P.band_rows, key.row0 = row0, key.row1 = row1;
-      for (auto& c : s.sched)
-        if (c->key == key) se = c.get();
-      if (!se) {
-        if (s.sched.size() >= kSchedEntries) {  // evict the entry used longest ago
-          size_t victim = 0;
-          for (size_t k = 1; k < s.sched.size(); ++k)
-            if (s.sched[k]->last_use < s.sched[victim]->last_use) victim = k;
-          s.sched.erase(s.sched.begin() + (long)victim);
-        }
-        s.sched.emplace_back(new SchedEntry());
-        se = s.sched.back().get();
-        se->key = key;
-      }
-      se->last_use = ++s.sched_clock;
+      se = find_sched(s, key);
     }
-    const cudaError_t le = launch_raycast(P, e - b, mode, stream, &l, counter, s.resident_ctas, ctx->opt, se);
-    if (le == cudaSuccess && se && P.next_list) se->launched();
+    const cudaError_t le = launch_raycast(P, e - b, mode, stream, &l, counter, s.resident_ctas, ctx->opt, se, sched_call);
+    if (le == cudaSuccess && se && P.next_list && !sched_call) se->launched();  // (a chunked frame: the caller, after its last chunk)
     if (le != cudaSuccess) {
       if (launch_states) (void)cudaFreeAsync(launch_states, stream);
       return fail_cuda(ctx, le, "launch_raycast");
@@ -778,6 +775,26 @@ static int launch_on(WxContext* ctx, int dev_i, const WxTree* tree, const WxStat
   if (launch_states) WX_CUDA(ctx, cudaFreeAsync(launch_states, stream));
   *launches_out = total_launches;
   return WX_OK;
+}
+
+// The long-tiles-first entry of a launch geometry on a stream (created on first use; the entry used longest ago makes room).
+static SchedEntry* find_sched(DeviceSlot& s, const SchedKey& key) {
+  SchedEntry* se = nullptr;
+  for (auto& c : s.sched)
+    if (c->key == key) se = c.get();
+  if (!se) {
+    if (s.sched.size() >= kSchedEntries) {
+      size_t victim = 0;
+      for (size_t k = 1; k < s.sched.size(); ++k)
+        if (s.sched[k]->last_use < s.sched[victim]->last_use) victim = k;
+      s.sched.erase(s.sched.begin() + (long)victim);
+    }
+    s.sched.emplace_back(new SchedEntry());
+    se = s.sched.back().get();
+    se->key = key;
+  }
+  se->last_use = ++s.sched_clock;
+  return se;
 }
 
 static bool shard_ok(const WxShard* shard) {
@@ -1043,6 +1060,30 @@ extern "C" int wx_render(WxContext* ctx, const WxTree* tree, const WxState* stat
       }
       // A chunk ends with a drain as long as its longest ray; chunks therefore alternate over three streams, so
       // that the next chunk fills the SMs the previous one is leaving.
+      // Long tiles first, once per FRAME: a list per chunk launch costs a second launch and a fork / join each (measured 0.855 vs
+      // 0.820 ms of kernels per 4K frame), so the whole frame's long tiles are rendered by one long-tile kernel ahead of the chunk
+      // launches, which skip them (tile ids are the frame's) and record the next frame's list between them.
+      SchedEntry* fse = nullptr;
+      bool long_launched = false;
+      SchedCall call_chunk;
+      call_chunk.phase = kSchedChunk, call_chunk.frame_tile_rows = (height + raycast_tile_height() - 1) / raycast_tile_height();
+      if (n_states == 1 && ctx->opt.long_first && ctx->opt.kernel == 0 && raycast_tile_height() == (uint32_t)kBandRowsMultiple) {
+        SchedKey key;
+        memset(&key, 0, sizeof(key));
+        key.tree = tree, key.stream = d0.stream, key.width = width, key.height = height, key.cam0 = 0, key.ncam = 1;
+        key.shard_index = 0, key.shard_count = 1;
+        fse = find_sched(d0, key);
+        SchedCall call_long;
+        call_long.phase = kSchedLongOnly;
+        uint32_t l = 0;
+        rc = launch_on(ctx, 0, tree, states, n_states, width, height, ctx->fb.rgba, nullptr, nullptr, d0.stream, &l, 0, 0xffffffffu, 0, 0, true, true,
+                       fse, &call_long);
+        if (rc) return rc;
+        launches += l;
+        long_launched = l != 0;
+        if (!fse->prepared) fse = nullptr;  // not applicable to this frame (render mode, size): plain chunk launches
+        else if (long_launched) WX_CUDA(ctx, fse->finish(d0.copy_stream));  // no chunk leaves before the long tiles are rendered
+      }
       WX_CUDA(ctx, cudaEventRecord(d0.fork, d0.stream));
       cudaStream_t ks[3] = {d0.stream, d0.aux[0], d0.aux[1]};
       for (int k = 0; k < 2; ++k) WX_CUDA(ctx, cudaStreamWaitEvent(d0.aux[k], d0.fork, 0));
@@ -1050,10 +1091,9 @@ extern "C" int wx_render(WxContext* ctx, const WxTree* tree, const WxState* stat
         const Chunk& ch = chunks[c];
         cudaStream_t st = ks[c % 3];
         uint32_t l = 0;
-        // (no long-tiles-first here: the chunks already overlap each other's drain over three streams, and a list per chunk costs
-        // a second launch and a fork / join each -- measured 0.855 vs 0.820 ms of kernels per 4K frame)
+        call_chunk.tile_row_offset = ch.row0 / raycast_tile_height();
         rc = launch_on(ctx, 0, tree, states, n_states, width, height, ctx->fb.rgba, nullptr, nullptr, st, &l, ch.cam0, ch.ncam,
-                       ch.row0, ch.row1, true, false);
+                       ch.row0, ch.row1, true, false, fse, fse ? &call_chunk : nullptr);
         if (rc) return rc;
         launches += l;
         WX_CUDA(ctx, cudaEventRecord(d0.chunk_done[c], st));
@@ -1066,6 +1106,10 @@ extern "C" int wx_render(WxContext* ctx, const WxTree* tree, const WxState* stat
       for (int k = 0; k < 2; ++k) {
         WX_CUDA(ctx, cudaEventRecord(d0.join[k], d0.aux[k]));
         WX_CUDA(ctx, cudaStreamWaitEvent(d0.stream, d0.join[k], 0));
+      }
+      if (fse) {
+        if (long_launched) WX_CUDA(ctx, fse->finish(d0.stream));
+        fse->launched();
       }
       WX_CUDA(ctx, cudaEventRecord(d0.ev1, d0.stream));
       WX_CUDA(ctx, cudaEventRecord(d0.fork, d0.copy_stream));

@@ -172,6 +172,9 @@ struct RenderParams {
   uint32_t* next_list;
   uint32_t* next_flag;
   uint32_t sched_cap, sched_threshold;
+  // A launch that renders only a row chunk of the frame the lists describe (wx_render's pipelined read-back): tile ids are those of
+  // the whole frame -- frame_tile_rows tile rows, this launch's first one being tile_row_offset.  0 / 0: the launch is the frame.
+  uint32_t frame_tile_rows, tile_row_offset;
 };
 // MARCH template parameter of the kernels: how hdda_ray is evaluated (WX_OPT_MARCH)
 constexpr int kMarchExact = 0, kMarchTolerance = 1;

@@ -25,12 +25,23 @@ struct LaunchOptions {
 // Long-tiles-first state of one launch geometry on one stream (wx_api.cu owns the objects; wx_raycast.cu drives them).
 struct TileSched {
   virtual cudaError_t prepare(RenderParams& P, uint32_t n_cams, uint32_t n_tiles, cudaStream_t stream, cudaStream_t* long_stream) = 0;
+  virtual void attach(RenderParams& P) = 0;  // the lists prepare() set up for this frame, for a launch that renders part of it
   virtual cudaError_t finish(cudaStream_t stream) = 0;
   virtual ~TileSched() {}
 };
+// How a launch takes part in the long-tiles-first scheme: the whole frame in one launch (list prepared, long-tile kernel, main
+// grid, joined); or a frame whose main grid is launched in row chunks (wx_render's pipelined read-back): first kSchedLongOnly
+// with the whole frame's geometry (list prepared, long-tile kernel only), then one kSchedChunk launch per row chunk.
+enum { kSchedWhole = 0, kSchedLongOnly = 1, kSchedChunk = 2 };
+struct SchedCall {
+  int phase = kSchedWhole;
+  uint32_t frame_tile_rows = 0, tile_row_offset = 0;  // kSchedChunk
+};
 cudaError_t launch_raycast(RenderParams& P, uint32_t n_cams, uint32_t render_mode, cudaStream_t stream, uint32_t* launches,
-                           uint32_t* work_counter, uint32_t resident_ctas, const LaunchOptions& opt, TileSched* sched = nullptr);
+                           uint32_t* work_counter, uint32_t resident_ctas, const LaunchOptions& opt, TileSched* sched = nullptr,
+                           const SchedCall* call = nullptr);
 constexpr uint32_t kCtasPerSm = 9;
+uint32_t raycast_tile_height();  // rows of a CTA's footprint (8 in the default build)
 // RGBA8 (linear) -> RGB8 through recorder.rs' linear_to_srgb; rgba_dev must be 16-byte aligned, rgb_dev 4-byte aligned.
 cudaError_t launch_srgb_rgb8(const uint8_t* rgba_dev, uint8_t* rgb_dev, size_t n_pixels, cudaStream_t stream);
 void build_srgb_lut(uint8_t lut[256]);

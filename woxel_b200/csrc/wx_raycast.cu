@@ -73,7 +73,7 @@ template <int MODE, bool AOV, int MARCH>
 __device__ __forceinline__ void tiled_body(const RenderParams& P) {
   const uint32_t tx = outside_in(blockIdx.x, gridDim.x);
   const uint32_t trow = outside_in(blockIdx.y, gridDim.y);      // tile row among the rows this launch owns
-  const uint32_t tile_id = (blockIdx.z * gridDim.y + trow) * gridDim.x + tx;
+  const uint32_t tile_id = (blockIdx.z * (P.frame_tile_rows ? P.frame_tile_rows : gridDim.y) + trow + P.tile_row_offset) * gridDim.x + tx;
   if (P.prev_flag != nullptr && __ldg(P.prev_flag + tile_id) != 0u) return;  // rendered by the long-tile kernel of this launch
   render_tile<MODE, AOV, MARCH>(P, tx, trow, blockIdx.z, tile_id);
 }
@@ -198,8 +198,9 @@ static cudaError_t launch_mode_persistent(const RenderParams& P, unsigned ctas, 
 // resident CTAs per SM.
 // long_stream != nullptr (and P.prev_list set): the long-tile kernel goes first, on that (high-priority) stream; the caller has
 // ordered it after `stream`'s earlier work and joins it afterwards.
+// main_grid == false: only the long-tile kernel (the first phase of a frame whose main grid is launched in row chunks).
 template <int MODE>
-static cudaError_t launch_mode(const RenderParams& P, dim3 grid, cudaStream_t stream, size_t pad, cudaStream_t long_stream) {
+static cudaError_t launch_mode(const RenderParams& P, dim3 grid, cudaStream_t stream, size_t pad, cudaStream_t long_stream, bool main_grid) {
   if (pad > 48 * 1024) {
     (void)cudaFuncSetAttribute(raycast_kernel<MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pad);
     (void)cudaFuncSetAttribute(raycast_kernel<MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pad);
@@ -208,16 +209,18 @@ static cudaError_t launch_mode(const RenderParams& P, dim3 grid, cudaStream_t st
     if (P.has_aov) raycast_long_tiles<MODE, true><<<P.sched_cap, kThreads, 0, long_stream>>>(P);
     else raycast_long_tiles<MODE, false><<<P.sched_cap, kThreads, 0, long_stream>>>(P);
   }
+  if (!main_grid) return cudaGetLastError();
   if (P.has_aov) raycast_kernel<MODE, true><<<grid, kThreads, pad, stream>>>(P);
   else raycast_kernel<MODE, false><<<grid, kThreads, pad, stream>>>(P);
   return cudaGetLastError();
 }
 template <int MODE>
-static cudaError_t launch_mode_tol(const RenderParams& P, dim3 grid, cudaStream_t stream, cudaStream_t long_stream) {
+static cudaError_t launch_mode_tol(const RenderParams& P, dim3 grid, cudaStream_t stream, cudaStream_t long_stream, bool main_grid) {
   if (long_stream != nullptr && P.prev_list != nullptr) {
     if (P.has_aov) raycast_long_tiles_tol<MODE, true><<<P.sched_cap, kThreads, 0, long_stream>>>(P);
     else raycast_long_tiles_tol<MODE, false><<<P.sched_cap, kThreads, 0, long_stream>>>(P);
   }
+  if (!main_grid) return cudaGetLastError();
   if (P.has_aov) raycast_kernel_tol<MODE, true><<<grid, kThreads, 0, stream>>>(P);
   else raycast_kernel_tol<MODE, false><<<grid, kThreads, 0, stream>>>(P);
   return cudaGetLastError();
@@ -227,13 +230,15 @@ static cudaError_t launch_mode_tol(const RenderParams& P, dim3 grid, cudaStream_
 // CTA-level queue 1.985 ms (profiles/r2_cta_queue.txt) -- the CTA tail the queues remove is not what limits the tiled grid,
 // so the simpler kernel is the default.
 
+uint32_t raycast_tile_height() { return (uint32_t)kTileH; }
+
 // Fills the launch geometry of P (shard -> bands -> tile rows) and launches frames
 // [P.cam_base, P.cam_base + n_cams) in render mode `render_mode` (the caller groups a camera batch
 // by mode).  P.n_states is the total number of states behind P.states / P.s0.
 // sched (optional): prepares the long-tiles-first list for this launch geometry (sched->prepare fills P.prev_* / P.next_*
 // and returns the stream of the long-tile kernel, already ordered after `stream`; sched->finish joins it back).
 cudaError_t launch_raycast(RenderParams& P, uint32_t n_cams, uint32_t render_mode, cudaStream_t stream, uint32_t* launches,
-                           uint32_t* work_counter, uint32_t resident_ctas, const LaunchOptions& opt, TileSched* sched) {
+                           uint32_t* work_counter, uint32_t resident_ctas, const LaunchOptions& opt, TileSched* sched, const SchedCall* call) {
   *launches = 0;
   if (P.shard_count == 0) P.shard_count = 1, P.shard_index = 0;
   if (P.row_end == 0 || P.row_end > P.height) P.row_end = P.height;
@@ -284,32 +289,46 @@ cudaError_t launch_raycast(RenderParams& P, uint32_t n_cams, uint32_t render_mod
   *launches = 1;
   cudaStream_t long_stream = nullptr;
   const uint64_t n_tiles = (uint64_t)P.tiles_x * tile_rows * n_cams;
+  const int phase = call ? call->phase : kSchedWhole;
+  P.frame_tile_rows = 0, P.tile_row_offset = 0;
+  bool main_grid = true;
   // (modes 3 and 4 spend most of their time in secondary rays, which the primary ray's iteration count does not predict:
   // measured no gain there, profiles/r2_longfirst.txt)
-  if (sched != nullptr && opt.long_first && render_mode <= 2u && n_tiles >= 512 && n_tiles < (1ull << 31)) {
+  if (phase == kSchedChunk) {  // a row chunk of a frame whose lists kSchedLongOnly prepared (or declined to)
+    if (sched != nullptr) {
+      P.sched_threshold = opt.long_threshold;
+      P.frame_tile_rows = call->frame_tile_rows, P.tile_row_offset = call->tile_row_offset;
+      sched->attach(P);
+    }
+  } else if (sched != nullptr && opt.long_first && render_mode <= 2u && n_tiles >= 512 && n_tiles < (1ull << 31)) {
     P.sched_threshold = opt.long_threshold;
     cudaError_t e = sched->prepare(P, n_cams, (uint32_t)n_tiles, stream, &long_stream);
     if (e != cudaSuccess) return e;
     if (long_stream != nullptr) *launches = 2;
   }
+  if (phase == kSchedLongOnly) {
+    main_grid = false;
+    *launches = long_stream != nullptr ? 1 : 0;
+    if (long_stream == nullptr) return cudaSuccess;  // no list yet (or not applicable): the chunks render everything
+  }
   cudaError_t le;
   if (opt.march == kMarchTolerance && render_mode != 2u) {  // mode 2 colours the iteration count: always exact
     switch (render_mode) {
-      case 1: le = launch_mode_tol<1>(P, grid, stream, long_stream); break;
-      case 3: le = launch_mode_tol<3>(P, grid, stream, long_stream); break;
-      case 4: le = launch_mode_tol<4>(P, grid, stream, long_stream); break;
-      default: le = launch_mode_tol<0>(P, grid, stream, long_stream); break;
+      case 1: le = launch_mode_tol<1>(P, grid, stream, long_stream, main_grid); break;
+      case 3: le = launch_mode_tol<3>(P, grid, stream, long_stream, main_grid); break;
+      case 4: le = launch_mode_tol<4>(P, grid, stream, long_stream, main_grid); break;
+      default: le = launch_mode_tol<0>(P, grid, stream, long_stream, main_grid); break;
     }
   } else {
     switch (render_mode) {
-      case 1: le = launch_mode<1>(P, grid, stream, opt.smem_pad, long_stream); break;
-      case 2: le = launch_mode<2>(P, grid, stream, opt.smem_pad, long_stream); break;
-      case 3: le = launch_mode<3>(P, grid, stream, opt.smem_pad, long_stream); break;
-      case 4: le = launch_mode<4>(P, grid, stream, opt.smem_pad, long_stream); break;
-      default: le = launch_mode<0>(P, grid, stream, opt.smem_pad, long_stream); break;  // Gray and the shader's `default:` arms
+      case 1: le = launch_mode<1>(P, grid, stream, opt.smem_pad, long_stream, main_grid); break;
+      case 2: le = launch_mode<2>(P, grid, stream, opt.smem_pad, long_stream, main_grid); break;
+      case 3: le = launch_mode<3>(P, grid, stream, opt.smem_pad, long_stream, main_grid); break;
+      case 4: le = launch_mode<4>(P, grid, stream, opt.smem_pad, long_stream, main_grid); break;
+      default: le = launch_mode<0>(P, grid, stream, opt.smem_pad, long_stream, main_grid); break;  // Gray and the shader's `default:` arms
     }
   }
-  if (le == cudaSuccess && long_stream != nullptr) le = sched->finish(stream);
+  if (le == cudaSuccess && long_stream != nullptr && phase == kSchedWhole) le = sched->finish(stream);  // (kSchedLongOnly: the caller joins)
   return le;
 }
 
