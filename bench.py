@@ -21,6 +21,14 @@ whole wx_render call), L2 is flushed (256 MiB write) before every timed step out
 rank sums its K step times and the job's time is the MAX over ranks.
 `e2e` goes through wx_render with HOST buffers: state H2D + kernel + RGBA D2H into pinned memory.
 
+Beside the contract's keys the line carries: `value_tolerance_mode` (+ `tolerance_mode_vs_oracle`: agreement figures and the
+listed mismatches against the oracle at full size, N = 1) for the opt-in WX_OPT_MARCH = 1; `secondary_ray_modes` (modes 3 / 4 in
+primary + secondary rays/s, N = 1); at N > 1 `strong_single_frame` (ONE frame tile-partitioned over the ranks through
+wx_render_shard, device-timed, bit-checked), `parity_vs_oracle_ranks` (the gathered slots of ranks 0, 1, N-1 against the oracle's
+render of each camera) and `gathered_frames_equal_every_ranks_own`; `e2e.host_ingest_GBs` (what the host ingests from N
+concurrent frame copies, measured in the run) and `e2e.frac_of_host_ingest`; `roofline.traffic_stale` (the ncu figures of
+profiles/traffic.json belong to another build of the kernel).
+
 The oracle (oracle/, a CPU restatement of the reference shader) is used here only for the reported
 `cpu_baseline` and for `--impl reference`; the reference itself (Rust + wgpu) cannot run in this image.
 """
@@ -478,15 +486,22 @@ def main():
     # ---- N > 1: (a) every rank's gathered frame is on GPU 0 -- rank 0 reads back the slots of ranks 0, 1 and N-1 for the oracle
     # check below; (b) strong scaling of ONE frame (BASELINE config 4's tile partition): camera 0's frame in 8-row bands dealt
     # round-robin to the ranks, every rank delivering its rows into the frame on GPU 0 (wx_render_shard), device-timed per rank.
-    rank_frames, strong = {}, None
+    rank_frames, strong, gather_ok = {}, None, None
     if world > 1:
         sync_all()
+        # every rank's own frame (its e2e render of the same camera, in host memory) against what arrived in its slot on GPU 0
+        mine = torch.tensor([checksum], dtype=torch.int64, device="cuda")
+        sums = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(sums, mine)
         if rank == 0:
-            for r in sorted({0, 1, world - 1}):
+            gather_ok = True
+            for r in range(world):
                 buf = np.empty((HEIGHT, WIDTH, 4), np.uint8)
                 ctx.check(lib.wx_memcpy_d2h(ctx._h, 0, buf.ctypes.data, C.c_void_p(stack.value + r * frame_bytes), frame_bytes, None))
                 ctx.check(lib.wx_stream_synchronize(ctx._h, 0, None))
-                rank_frames[r] = buf
+                gather_ok = gather_ok and int(buf.view(np.uint32).sum(dtype=np.uint64)) == int(sums[r].item())
+                if r in (0, 1, world - 1):
+                    rank_frames[r] = buf
         sync_all()
         state0 = make_state(args.scene, 0)
         # one GPU alone: kernel time of the whole frame, same kernel, local output
@@ -625,6 +640,7 @@ def main():
             "value_tolerance_mode": round(value_tol, 1), "tolerance_mode_ms_per_step": round(tol_ms, 4),
             "tolerance_mode_vs_oracle": tol_fig, "secondary_ray_modes": modes,
             "strong_single_frame": strong, "parity_vs_oracle_ranks": parity_ranks,
+            "gathered_frames_equal_every_ranks_own": gather_ok,  # N > 1: checksum of every slot on GPU 0 == the rank's own host frame
             "wall_ms_per_step_incl_flush": round(1e3 * wall / args.steps, 4),
             "per_rank_ms_per_step": [round(x, 4) for x in per_rank],  # ms_per_step is their maximum
             "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": 256 * world, "d2h_bytes_per_step": frame_bytes * world,
