@@ -10,7 +10,8 @@ import woxel_b200 as W
 from woxel_b200 import _ffi
 
 lib = _ffi.cuda_lib()
-ctx = W.Context()
+import knobs
+ctx = knobs.apply_env(W.Context())
 
 
 def upload_product(v):

@@ -57,8 +57,7 @@ struct SchedEntry final : TileSched {
   void release() {
     if (ls) (void)cudaStreamSynchronize(ls);
     for (int k = 0; k < 2; ++k) {
-      if (list[k]) (void)cudaFree(list[k]);
-      if (flag[k]) (void)cudaFree(flag[k]);
+      if (flag[k]) (void)cudaFree(flag[k]);  // (list[k] points into the same allocation)
       list[k] = flag[k] = nullptr;
     }
     n_tiles = cap = 0, valid = false, prepared = false;
@@ -83,9 +82,9 @@ struct SchedEntry final : TileSched {
     if (tiles != n_tiles) {
       release();
       n_tiles = tiles, cap = std::min<uint32_t>(std::max<uint32_t>(tiles / 16u, 64u), 4096u);
-      for (int k = 0; k < 2 && e == cudaSuccess; ++k) {
-        e = cudaMalloc(&list[k], ((size_t)cap + 1) * 4);
-        if (e == cudaSuccess) e = cudaMalloc(&flag[k], (size_t)n_tiles * 4);
+      for (int k = 0; k < 2 && e == cudaSuccess; ++k) {  // one allocation per set: [flags (n_tiles) | count | list (cap)] -- flags and count are zeroed together
+        e = cudaMalloc(&flag[k], ((size_t)n_tiles + 1 + cap) * 4);
+        list[k] = flag[k] ? flag[k] + n_tiles : nullptr;
       }
       if (e != cudaSuccess) {
         release();
@@ -93,8 +92,7 @@ struct SchedEntry final : TileSched {
       }
     }
     const int nxt = cur ^ 1;
-    e = cudaMemsetAsync(flag[nxt], 0, (size_t)n_tiles * 4, stream);
-    if (e == cudaSuccess) e = cudaMemsetAsync(list[nxt], 0, 4, stream);
+    e = cudaMemsetAsync(flag[nxt], 0, ((size_t)n_tiles + 1) * 4, stream);  // the flags and the count behind them
     if (e != cudaSuccess) return e;
     P.next_list = list[nxt], P.next_flag = flag[nxt];
     P.sched_cap = cap;  // (P.sched_threshold: the launcher's option)
