@@ -233,7 +233,8 @@ static cudaError_t launch_mode_tol(const RenderParams& P, dim3 grid, cudaStream_
 uint32_t raycast_tile_height() { return (uint32_t)kTileH; }
 // The list costs one memset, a fork / join and a second (mostly empty) launch per launch, ~8 us: worth it on a 4K frame (0.76 ms:
 // -5 %) and on one rank's share of a 4K frame (0.18 -> 0.155 ms), not on a 1080p frame (0.10 ms: +5...10 %,
-// profiles/r2_longfirst.txt).  The criterion is therefore the size of the FRAME, not of the launch.
+// profiles/r2_longfirst.txt).  The criterion is therefore the size of the FRAME (times the cameras of a batch: config 5's 64 x 1080p
+// launch gains 7 %), not of the launch.
 constexpr uint64_t kLongFirstMinPixels = 1ull << 22;
 
 // Fills the launch geometry of P (shard -> bands -> tile rows) and launches frames
@@ -304,7 +305,7 @@ cudaError_t launch_raycast(RenderParams& P, uint32_t n_cams, uint32_t render_mod
       P.frame_tile_rows = call->frame_tile_rows, P.tile_row_offset = call->tile_row_offset;
       sched->attach(P);
     }
-  } else if (sched != nullptr && opt.long_first && render_mode <= 2u && (uint64_t)P.width * P.height >= kLongFirstMinPixels && n_tiles >= 512 &&
+  } else if (sched != nullptr && opt.long_first && render_mode <= 2u && (uint64_t)P.width * P.height * n_cams >= kLongFirstMinPixels && n_tiles >= 512 &&
              n_tiles < (1ull << 31)) {
     P.sched_threshold = opt.long_threshold;
     cudaError_t e = sched->prepare(P, n_cams, (uint32_t)n_tiles, stream, &long_stream);
