@@ -22,7 +22,7 @@ rank sums its K step times and the job's time is the MAX over ranks.
 `e2e` goes through wx_render with HOST buffers: state H2D + kernel + RGBA D2H into pinned memory.
 
 Beside the contract's keys the line carries: `value_tolerance_mode` (+ `tolerance_mode_vs_oracle`: agreement figures and the
-listed mismatches against the oracle at full size, N = 1) for the opt-in WX_OPT_MARCH = 1; `secondary_ray_modes` (modes 3 / 4 in
+listed mismatches against the oracle at full size, N = 1) for the opt-in WX_OPT_MARCH = 2; `secondary_ray_modes` (modes 3 / 4 in
 primary + secondary rays/s, N = 1); at N > 1 `strong_single_frame` (ONE frame tile-partitioned over the ranks through
 wx_render_shard, device-timed, bit-checked), `parity_vs_oracle_ranks` (the gathered slots of ranks 0, 1, N-1 against the oracle's
 render of each camera) and `gathered_frames_equal_every_ranks_own`; `e2e.host_ingest_GBs` (what the host ingests from N
@@ -395,8 +395,8 @@ def main():
     timed_launches = launches[0]
     value = world * rays_per_frame / (ms_per_step * 1e-3) / 1e6
 
-    # ---- tolerance mode (WX_OPT_MARCH = 1: fused p += t * dir, rays start at the bounding box of the active cells): same loop
-    ctx.set_option(_ffi.WX_OPT_MARCH, 1)
+    # ---- tolerance mode (WX_OPT_MARCH = 2: fused p += t * dir, rays start at the bounding box of the active cells): same loop
+    ctx.set_option(_ffi.WX_OPT_MARCH, 2)
     tol_ms, _, _ = timed_run(3, args.steps)
     ctx.set_option(_ffi.WX_OPT_MARCH, 0)
     value_tol = world * rays_per_frame / (tol_ms * 1e-3) / 1e6
@@ -576,7 +576,7 @@ def main():
             else:
                 # tolerance mode against the oracle at full size: the north-star bar, mismatches listed
                 import agreement
-                ctx.set_option(_ffi.WX_OPT_MARCH, 1)
+                ctx.set_option(_ffi.WX_OPT_MARCH, 2)
                 t_rgba, t_aov = ctx.render(tree, state, WIDTH, HEIGHT, aov=True)
                 ctx.set_option(_ffi.WX_OPT_MARCH, 0)
                 _, ref_aov, _ = gd.render(oracle_state(state), WIDTH, HEIGHT, aov=True, threads=cores)
@@ -636,7 +636,7 @@ def main():
                      "device_MB": round(tree.info.device_bytes / 1e6, 1)},
             "prep_s": prep,
             "value_warm_l2": round(world * rays_per_frame / (warm_ms * 1e-3) / 1e6, 1),
-            # the opt-in tolerance mode (WX_OPT_MARCH = 1), same timed loop; `value` above is the exact (bit-identical) kernel
+            # the opt-in tolerance mode (WX_OPT_MARCH = 2), same timed loop; `value` above is the exact (bit-identical) kernel
             "value_tolerance_mode": round(value_tol, 1), "tolerance_mode_ms_per_step": round(tol_ms, 4),
             "tolerance_mode_vs_oracle": tol_fig, "secondary_ray_modes": modes,
             "strong_single_frame": strong, "parity_vs_oracle_ranks": parity_ranks,

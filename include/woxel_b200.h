@@ -221,9 +221,13 @@ int wx_last_render_info(const WxContext *ctx, WxRenderInfo *info);
 typedef enum WxOption {
   WX_OPT_MARCH = 1,         /* 0 (default): exact -- frames and AOVs bit-identical to the strict-f32 restatement of the shader.
                                1: tolerance mode -- the north-star bar (hit voxel + leaf equal on >= 99.9 % of the pixels, depth
-                               within 1e-4 relative, RGB within 1/255) instead of bit identity: p += t * dir may be one fused
-                               multiply-add and rays start at their entry into the active bounding box.  Render mode 2 (Ray:
-                               colours the iteration count) always takes the exact march. */
+                               within 1e-4 relative, RGB within 1/255) instead of bit identity: p += t * dir is one fused
+                               multiply-add per axis.
+                               2: 1 + rays start at their entry into the bounding box of the active cells.  Meets the bar on
+                               scenes whose rays mostly hit or miss the box (the benchmark scenes: 99.98 %), NOT on sparse scenes
+                               where many rays cross the box and leave (94-98 %: their out-of-bounds colour depends on the axis
+                               of the LAST step, which changes with the start point).  Measurement only.
+                               Render mode 2 (Ray: colours the iteration count) always takes the exact march. */
   WX_OPT_KERNEL = 2,        /* 0 (default): tiled grid; 1: persistent kernel, warp-level tile queue; 2: persistent kernel,
                                CTA-level chunk queue.  Same results; measured slower (profiles/). */
   WX_OPT_RENDER_CHUNKS = 3, /* row chunks of a pipelined wx_render (0 = automatic) */

@@ -19,10 +19,10 @@ thread_local WxEmuTrace* wx_emu_trace = nullptr;
 namespace {
 using namespace wx;
 
-int g_march = 0;  // wxe_set_march: 0 exact, 1 tolerance mode (WX_OPT_MARCH); like the launcher, mode 2 always runs exact
+int g_march = 0;  // wxe_set_march: 0 exact, 1 tolerance mode, 2 tolerance mode + bounding-box clip (WX_OPT_MARCH); like the launcher, mode 2 always runs exact
 template <int MODE>
 void pixel(const RenderParams& P, const PixelRef& q) {
-  if (g_march == kMarchTolerance && MODE != 2) {
+  if (g_march != kMarchExact && MODE != 2) {
     if (P.has_aov) render_pixel<MODE, true, kMarchTolerance>(P, q);
     else render_pixel<MODE, false, kMarchTolerance>(P, q);
     return;
@@ -79,7 +79,7 @@ struct EmuScene {
     int32_t bbox[6] = {1 << 30, 1 << 30, 1 << 30, -1, -1, -1};
     if (with_grid) build_grid_tables(d->n5, d->n4, origins, root_grid, e5.data(), e4.data(), grid, f4), grid_bbox_cells(grid, bbox);
     fill_dev_tree(P.tree, e5.data(), e4.data(), l3.data(), origins.data(), d->n5, d->n4, d->n3, leaf_bits == 8 ? 9 : 11, fast_ok, root_grid,
-                  with_grid ? grid.data() : nullptr, with_grid ? f4.data() : nullptr, bbox);
+                  with_grid ? grid.data() : nullptr, with_grid ? f4.data() : nullptr, g_march == 2 ? bbox : nullptr);
     P.n_states = n_states;
     P.states = states;
     P.s0 = states[0];

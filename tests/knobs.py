@@ -15,8 +15,8 @@ def apply_env(ctx):
         ctx.set_option(_ffi.WX_OPT_RENDER_CHUNKS, int(os.environ["WX_RENDER_CHUNKS"]))
     if os.environ.get("WX_SMEM_PAD"):
         ctx.set_option(_ffi.WX_OPT_SMEM_PAD, int(os.environ["WX_SMEM_PAD"]))
-    if os.environ.get("WX_MARCH") == "tolerance":
-        ctx.set_option(_ffi.WX_OPT_MARCH, 1)
+    if os.environ.get("WX_MARCH") in ("tolerance", "tolerance_clip"):
+        ctx.set_option(_ffi.WX_OPT_MARCH, 1 if os.environ["WX_MARCH"] == "tolerance" else 2)
     if os.environ.get("WX_LONG_FIRST") in ("0", "1"):
         ctx.set_option(_ffi.WX_OPT_LONG_FIRST, int(os.environ["WX_LONG_FIRST"]))
     if os.environ.get("WX_LONG_THRESHOLD"):

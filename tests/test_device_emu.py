@@ -277,22 +277,47 @@ def test_wide_distances_take_the_right_march(what):
 
 
 def test_tolerance_mode_meets_the_north_star_bar():
-    """WX_OPT_MARCH = 1 (fused p += t * dir, rays start at the bounding box of the active cells) is not bit-identical -- it must
-    meet the north-star bar against the oracle instead: hit voxel + leaf (and colour within 1/255) equal on >= 99.9 % of the
-    dispatched pixels, depth within 1e-4 relative; and it must actually skip steps.  Mode 2 stays exact."""
+    """WX_OPT_MARCH = 1 (fused p += t * dir) and 2 (+ rays start at the bounding box of the active cells) are not bit-identical --
+    they must meet the north-star bar against the oracle instead: hit voxel + leaf (and colour within 1/255) equal on >= 99.9 % of
+    the dispatched pixels, depth within 1e-4 relative; and 2 must actually skip steps.  Mode 2 stays exact.  (Scenes whose tree
+    covers the world, like every BASELINE scene.  On a sparse scene with missing N5s -- `single_voxel`, `offcentre_sphere` -- rays
+    leave through level-0 lattice planes that coincide with the +-4096 world boundary, a knife edge for ANY change of rounding:
+    94-96 % there, see test_tolerance_mode_on_sparse_scenes_is_reported_not_asserted.)"""
     import agreement
     for name, cam in (("cube", "oblique_a"), ("icosahedron", "oblique_b"), ("cube", "default")):
         s = scenes.get_scene(name)
         for mode in (0, 3, 4):
             st = scenes.state_for(*scenes.CAMERAS[cam], 384, 216, mode=mode)
-            rgba, aov, _ = E.render(s.desc(), st, 384, 216, march=1)
             ref_rgba, ref_aov, _ = s.gpu.render(st, 384, 216)
-            fig = agreement.compare(rgba[0], {k: v[0] for k, v in aov.items()}, ref_rgba, ref_aov)
-            assert agreement.meets_bar(fig), (name, cam, mode, fig)
-            assert fig["mismatch_pixels"] <= len(fig["mismatches_listed"]) or fig["mismatch_pixels"] < 0.001 * fig["pixels"]
             hit = ref_aov["state"] == 0
-            assert aov["iters"][0][hit].mean() < ref_aov["iters"][hit].mean() - 0.5, "the bounding-box clip skipped nothing"
+            for march in (1, 2):  # 1: fused p += t * dir; 2: + rays start at the bounding box of the active cells
+                rgba, aov, _ = E.render(s.desc(), st, 384, 216, march=march)
+                fig = agreement.compare(rgba[0], {k: v[0] for k, v in aov.items()}, ref_rgba, ref_aov)
+                assert agreement.meets_bar(fig), (name, cam, mode, march, fig)
+                assert fig["mismatch_pixels"] <= len(fig["mismatches_listed"]) or fig["mismatch_pixels"] < 0.001 * fig["pixels"]
+                if march == 2:
+                    assert aov["iters"][0][hit].mean() < ref_aov["iters"][hit].mean() - 0.5, "the bounding-box clip skipped nothing"
+                else:
+                    assert abs(aov["iters"][0][hit].mean() - ref_aov["iters"][hit].mean()) < 0.05
         st = scenes.state_for(*scenes.CAMERAS[cam], 192, 108, mode=2)
-        rgba, aov, _ = E.render(s.desc(), st, 192, 108, march=1)
+        rgba, aov, _ = E.render(s.desc(), st, 192, 108, march=2)
         ref_rgba, ref_aov, _ = s.gpu.render(st, 192, 108)
         assert np.array_equal(rgba[0], ref_rgba) and np.array_equal(aov["iters"][0], ref_aov["iters"])
+
+
+def test_tolerance_mode_on_sparse_scenes_is_reported_not_asserted():
+    """What the tolerance mode does NOT promise: in a tree with missing N5s the empty space is stepped through in 4096-voxel
+    lattice cells whose planes coincide with the world boundary (|p| > 4096 ends a ray), so whether a ray ends on this step or the
+    next -- and with which axis mask, i.e. which out-of-bounds colour -- flips with one ulp of p.  Fused multiply-adds change a
+    few per cent of those pixels (any contracting WGSL compiler would): hits still agree, the out-of-bounds shade does not."""
+    import agreement
+    s = scenes.get_scene("offcentre_sphere")
+    st = scenes.state_for(*scenes.CAMERAS["oblique_a"], 384, 216, mode=0)
+    ref_rgba, ref_aov, _ = s.gpu.render(st, 384, 216)
+    rgba, aov, _ = E.render(s.desc(), st, 384, 216, march=1)
+    fig = agreement.compare(rgba[0], {k: v[0] for k, v in aov.items()}, ref_rgba, ref_aov)
+    hit = ref_aov["state"] == 0
+    hits_equal = ((aov["voxel"][0] == ref_aov["voxel"]).all(-1) & (aov["leaf"][0] == ref_aov["leaf"]))[hit].mean()
+    assert hits_equal >= 0.999 and fig["depth_rel_over_1e-4_pixels"] == 0
+    assert 0.90 < fig["voxel_leaf_agree_frac"] < 0.999  # the out-of-bounds shade of a few per cent of the pixels differs
+    assert (aov["state"][0] == ref_aov["state"]).mean() > 0.9999

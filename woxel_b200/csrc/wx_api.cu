@@ -712,7 +712,7 @@ static int launch_on(WxContext* ctx, int dev_i, const WxTree* tree, const WxStat
   RenderParams P;
   memset(&P, 0, sizeof(P));
   fill_dev_tree(P.tree, o.e5, o.e4, o.l3, o.origins, tree->info.n5, tree->info.n4, tree->info.n3, tree->leaf_shift, tree->fast_ok,
-                tree->root_grid, o.grid, o.f4, tree->bbox_cells);
+                tree->root_grid, o.grid, o.f4, ctx->opt.march == 2 ? tree->bbox_cells : nullptr);  // the clip only with WX_OPT_MARCH = 2
   P.n_states = n_states;
   P.width = width, P.height = height;
   P.rgba = reinterpret_cast<uchar4*>(rgba_dev);
@@ -1230,7 +1230,7 @@ extern "C" int wx_set_option(WxContext* ctx, int option, int64_t value) {
   if (!ctx) return fail(nullptr, WX_ERR_INVALID_ARGUMENT, "wx_set_option: null context");
   switch (option) {
     case WX_OPT_MARCH:
-      if (value != 0 && value != 1) break;
+      if (value < 0 || value > 2) break;
       ctx->opt.march = (int)value;
       return WX_OK;
     case WX_OPT_KERNEL:

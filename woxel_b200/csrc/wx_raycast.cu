@@ -318,7 +318,7 @@ cudaError_t launch_raycast(RenderParams& P, uint32_t n_cams, uint32_t render_mod
     if (long_stream == nullptr) return cudaSuccess;  // no list yet (or not applicable): the chunks render everything
   }
   cudaError_t le;
-  if (opt.march == kMarchTolerance && render_mode != 2u) {  // mode 2 colours the iteration count: always exact
+  if (opt.march != kMarchExact && render_mode != 2u) {  // mode 2 colours the iteration count: always exact
     switch (render_mode) {
       case 1: le = launch_mode_tol<1>(P, grid, stream, long_stream, main_grid); break;
       case 3: le = launch_mode_tol<3>(P, grid, stream, long_stream, main_grid); break;
