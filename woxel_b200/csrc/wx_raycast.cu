@@ -153,8 +153,9 @@ __global__ void __launch_bounds__(kThreads, WX_MIN_BLOCKS) raycast_persistent(co
 }
 
 // ---------------------------------------------------------------------------------------------
-// Persistent kernel with a CTA-level chunk queue (WX_KERNEL=persistent_cta; EXPERIMENTAL: written when the round's GPU
-// time was spent -- compiled, not yet run or measured; tests/test_parity_gpu.py holds an opt-in bit-identity test).
+// Persistent kernel with a CTA-level chunk queue (WX_OPT_KERNEL = 2).  Measured in round 2 (profiles/r2_cta_queue.txt):
+// bit-identical (tests/test_parity_gpu.py::test_cta_queue_kernel_is_bit_identical) and 2.1x SLOWER than the tiled grid --
+// lane 0's ticket loop (a shared-memory atomic read and a CAS per tile) sits in front of every tile.  Kept selectable, not the default.
 // Why: in the tiled grid a CTA slot is held until its slowest warp ends (warp slots are 92.5 % used inside a CTA on the
 // bench frame, tools/warp_stats.py), and the warp-level queue above cures that but scatters the warps of a CTA over the
 // frame (their tiles no longer share nodes in L1).  Here the CTA owns a 32x16-pixel chunk; its warps take the chunk's 16
