@@ -757,7 +757,20 @@ struct GridRay {
     if (lvl == 4u) {
       const uint32_t e = __ldg(T.f4 + (uint32_t)((x >> 3) * 256u + (y >> 3) * 16u + (z >> 3) + w4));
       if ((int32_t)e >= 0) dbits = 8u, size = __uint_as_float(e), lvl = 0u;
-      else w3 = e << 3, lvl = 3u;
+      else {
+        w3 = e << 3, lvl = 3u;
+#if defined(WX_PREFETCH_LEAF) && !defined(WX_HOST_EMU)
+        // A/B experiment: on entering a leaf, pull its whole 512-byte brick (four 128-byte lines) towards L1 -- a ray that grazes the
+        // shell otherwise takes one L2 round trip per voxel it advances in x (a 32-byte sector holds 4 y x 8 z voxels of one x).
+        {
+          const uint8_t* brick = T.l3 + (uint32_t)(w3 + ((x & ~7u) * 64u + (y & ~7u) * 8u + (z & ~7u)));
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(brick));
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(brick + 128));
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(brick + 256));
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(brick + 384));
+        }
+#endif
+      }
     }
 #if defined(WX_STAGE_LEAF) && !defined(WX_HOST_EMU)
     // A/B EXPERIMENT (never the default; VERDICT r1 item 6, north_star "leaf bricks staged in shared memory, TMA where the layout
