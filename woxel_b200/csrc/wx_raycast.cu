@@ -19,7 +19,10 @@ namespace wx {
 #endif
 constexpr int kWarpW = WX_WARP_W, kWarpH = 32 / WX_WARP_W;
 // the warps of a CTA tile a 16-pixel-wide block (8 rows for 4 warps): row bands of 8 stay the sharding unit
-constexpr int kCtaWarpsX = (16 / kWarpW) < WX_CTA_WARPS ? (16 / kWarpW) : WX_CTA_WARPS;
+#ifndef WX_CTA_WARPS_X
+#define WX_CTA_WARPS_X ((16 / kWarpW) < WX_CTA_WARPS ? (16 / kWarpW) : WX_CTA_WARPS)  // A/B: 2 = the four warps as 2 x 2 (8 x 16 px)
+#endif
+constexpr int kCtaWarpsX = WX_CTA_WARPS_X;
 constexpr int kCtaWarpsY = WX_CTA_WARPS / kCtaWarpsX;
 constexpr int kTileW = kCtaWarpsX * kWarpW, kTileH = kCtaWarpsY * kWarpH;  // CTA footprint in pixels
 #define WX_LANE_X(warp, lane) (((warp) % kCtaWarpsX) * kWarpW + ((lane) % kWarpW))
