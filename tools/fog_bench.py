@@ -56,7 +56,8 @@ cams = {"outside": ((0.5, 0.5, -2.44140625 * half - 0.5), (0.5, 0.5, 0.5)),
         "inside": ((3.5, 2.5, 1.5), (0.78125 * half, 0.46875 * half, 0.625 * half))}
 ref_frames = {}
 for ndev in sorted({1, args.devices}):
-    ctx = W.Context(n_devices=ndev)
+    import knobs
+    ctx = knobs.apply_env(W.Context(n_devices=ndev))
     t0 = time.time()
     tree = ctx.build(desc)
     t_build = time.time() - t0
