@@ -55,7 +55,7 @@ typedef struct WxhVdbInfo {
 } WxhVdbInfo;
 int wxh_vdb_read(const char *path, const char *grid_name, WxhVdb **out, WxhVdbInfo *info);
 /* One c-blosc 1.x frame as the reader meets them inside a .vdb (src/vdb/read.rs:514-533 hands them to the c-blosc library):
- * BloscLZ, LZ4 and zlib codecs, byte or bit shuffle.  *out_len receives the decoded size; WXH_ERR_INVALID_ARGUMENT with
+ * BloscLZ, LZ4, Snappy, zlib and Zstd codecs, byte or bit shuffle.  *out_len receives the decoded size; WXH_ERR_INVALID_ARGUMENT with
  * *out_len set when `cap` is too small; WXH_ERR_BLOSC for a corrupt or unsupported frame. */
 int wxh_blosc_decompress(const uint8_t *frame, size_t n, uint8_t *out, size_t cap, size_t *out_len);
 

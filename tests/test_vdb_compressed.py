@@ -81,12 +81,15 @@ def test_blosc_multi_block_frames(tmp_path, blocksize):
         assert e.kind == "Leaf" and e.value == wbits
 
 
-@pytest.mark.parametrize("codec", ["blosclz", "zlib", "lz4"])
+@pytest.mark.parametrize("codec", ["blosclz", "zlib", "lz4", "snappy", "zstd"])
 @pytest.mark.parametrize("bit_shuffle", [False, True])
 @pytest.mark.parametrize("blocksize,half", [(None, True), (384, True), (1024, False), (4096, False)])
 def test_blosc_codecs_and_shuffles(tmp_path, codec, bit_shuffle, blocksize, half):
-    """The Blosc frame with each codec the reader decodes (BloscLZ = c-blosc's default codec, LZ4 = what OpenVDB writes, zlib)
-    and with byte or bit shuffle, single and multi-block, split and unsplit streams: the written voxels come back."""
+    """The Blosc frame with each codec c-blosc 1.x knows (BloscLZ = its default codec, LZ4 = what OpenVDB writes, Snappy, zlib, Zstd;
+    the Snappy and Zstd streams are written by libsnappy / libzstd through pyarrow) and with byte or bit shuffle, single and
+    multi-block, split and unsplit streams: the written voxels come back."""
+    if codec in ("snappy", "zstd"):
+        pytest.importorskip("pyarrow")
     pts, vals = sample_voxels(seed=5)
     path = str(tmp_path / "c.vdb")
     V.VdbWriter(compression=V.BLOSC | V.ACTIVE_MASK, half_float=half, blosc_blocksize=blocksize, blosc_codec=codec,
@@ -149,10 +152,12 @@ def test_compressed_model_renders(tmp_path):
     assert np.array_equal(fa.tab3[inactive], fb.tab3[inactive])
 
 
-@pytest.mark.parametrize("codec", ["blosclz", "lz4", "zlib"])
+@pytest.mark.parametrize("codec", ["blosclz", "lz4", "zlib", "snappy", "zstd"])
 def test_mutated_blosc_frames_never_crash(codec):
     """Bit flips, truncations and random words in Blosc frames of every codec: decoded bytes or a VdbError, never a crash or an
     over-read (this test is part of the ASan + UBSan run, tools/asan_host.sh)."""
+    if codec in ("snappy", "zstd"):
+        pytest.importorskip("pyarrow")
     rng = np.random.default_rng(17)
     base = (rng.integers(0, 4, 6000, dtype=np.uint8).astype(np.uint16) * 257).tobytes()
     frames = [V.blosc_compress(base, 2, codec=codec), V.blosc_compress(base, 2, codec=codec, bit_shuffle=True, blocksize=1024),
@@ -204,19 +209,28 @@ def test_crafted_blosc_header_is_rejected_before_any_allocation():
 
 def test_blosc_frames_with_streams_from_the_real_codec_libraries():
     """tests/golden/blosc_frames.npz (tests/golden/make_blosc_golden.py): frames whose compressed streams were produced by liblz4,
-    libsnappy (both through pyarrow) and zlib -- not by this repository's own encoders -- in every shuffle / block-size
+    libsnappy, libzstd (all three through pyarrow) and zlib -- not by this repository's own encoders -- in every shuffle / block-size
     combination.  The product decoder must return the payloads byte for byte.  (The frame CONTAINER is still written by
     tests/vdb_writer.py: c-blosc itself is not available in this image.)"""
     import os
     z = np.load(os.path.join(os.path.dirname(__file__), "golden", "blosc_frames.npz"))
     frames = [k for k in z.files if k.startswith("frame/")]
-    assert len(frames) >= 70
+    assert len(frames) >= 150
     seen = set()
     for k in frames:
         _, pname, codec, shuffle, _ = k.split("/")
         assert W.vdb.blosc_decompress(z[k].tobytes()) == z[f"payload/{pname}"].tobytes(), k
         seen.add((codec, shuffle))
-    assert seen >= {(c, s) for c in ("lz4", "snappy", "zlib") for s in ("none", "byte", "bit")}
+    assert seen >= {(c, s) for c in ("lz4", "snappy", "zlib", "zstd1", "zstd9", "zstd19") for s in ("none", "byte", "bit")}
+    # bare Zstandard frames of libzstd (levels -5 .. 22; multi-block inputs, RLE / raw / compressed blocks, 1- and 4-stream
+    # Huffman literals, FSE-coded and repeated tables) inside a one-stream Blosc frame
+    raw = [k for k in z.files if k.startswith("raw_zstd/")]
+    assert len(raw) >= 40
+    for k in raw:
+        data = z["payload/" + k.split("/")[1]].tobytes()
+        stream = z[k].tobytes()
+        frame = V.blosc_compress(data, 1, do_shuffle=False, codec="zstd", encode=lambda b: stream)
+        assert W.vdb.blosc_decompress(frame) == data, k
     # a real-library stream cut short or with a flipped byte is an error, never a crash or a wrong size
     k = "frame/sdf_f32/lz4/byte/0"
     good = bytearray(z[k].tobytes())

@@ -144,7 +144,13 @@ def shuffle(data: bytes, typesize: int) -> bytes:
     return head.tobytes() + a[n * typesize:].tobytes()
 
 
-BLOSC_CODECS = {"blosclz": 0, "lz4": 1, "snappy": 2, "zlib": 3}
+BLOSC_CODECS = {"blosclz": 0, "lz4": 1, "snappy": 2, "zlib": 3, "zstd": 4}
+
+
+def _pyarrow_codec(name: str):
+    """Snappy and Zstd have no encoder in this module: their streams come from libsnappy / libzstd through pyarrow."""
+    import pyarrow as pa
+    return lambda b: pa.compress(b, codec=name, asbytes=True)
 
 
 def blosc_compress(data: bytes, typesize: int, do_shuffle: bool = True, blocksize: int | None = None, force_memcpy: bool = False,
@@ -162,7 +168,8 @@ def blosc_compress(data: bytes, typesize: int, do_shuffle: bool = True, blocksiz
     # `encode`: the stream compressor; by default this module's own encoders -- tests/golden/make_blosc_golden.py passes the REAL
     # libraries' (liblz4 / libsnappy through pyarrow, zlib) so that the decoders are also checked against streams they did not write
     if encode is None:
-        encode = {"lz4": lz4_compress_block, "blosclz": blosclz_compress_block, "zlib": lambda b: zlib.compress(b, 6)}[codec]
+        encode = {"lz4": lz4_compress_block, "blosclz": blosclz_compress_block, "zlib": lambda b: zlib.compress(b, 6),
+                  "snappy": lambda b: _pyarrow_codec("snappy")(b), "zstd": lambda b: _pyarrow_codec("zstd")(b)}[codec]
     if force_memcpy or nbytes < 128:
         flags |= 2
         return struct.pack("<BBBBIII", 2, 1, flags, typesize, nbytes, blocksize, 16 + nbytes) + data

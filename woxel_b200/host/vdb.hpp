@@ -171,9 +171,9 @@ struct ArchiveHeader {
 };
 
 // .vdb reader (read.rs).  Supports what the reference supports: file versions >= 218, no / zlib /
-// Blosc(LZ4, BloscLZ, zlib codecs; byte shuffle) block compression, active-mask compression,
+// Blosc(BloscLZ, LZ4, Snappy, zlib, Zstd codecs; byte or bit shuffle) block compression, active-mask compression,
 // half-float storage.
-// Decodes one c-blosc 1.x frame (BloscLZ / LZ4 / zlib codec, byte or bit shuffle); throws VdbError.
+// Decodes one c-blosc 1.x frame (BloscLZ / LZ4 / Snappy / zlib / Zstd codec, byte or bit shuffle); throws VdbError.
 std::vector<uint8_t> decompress_blosc_frame(const uint8_t* frame, size_t n, size_t max_bytes = (size_t)-1);
 
 class VdbReader {

@@ -127,6 +127,8 @@ void VdbReader::parse_header() {  // read.rs:62-121, :166-212
   }
 }
 
+bool zstd_decompress_block(const uint8_t* src, size_t n, uint8_t* dst, size_t cap);  // zstd_dec.cpp
+
 namespace {
 
 // ---------------------------------------------------------------------------------------------
@@ -141,8 +143,7 @@ namespace {
 //           each an int32 byte count followed by the codec's output, or by the plain bytes when the count
 //           equals the stream size
 // OpenVDB writes these frames with blosc_compress_ctx(9, shuffle, sizeof(T), ..., "lz4"); LZ4, BloscLZ (c-blosc's default
-// codec) and zlib (through the system library) are decoded, with byte or bit shuffle; Snappy and Zstd report
-// UnsupportedBloscFormat.
+// codec), Snappy, Zstd (zstd_dec.cpp) and zlib (through the system library) are decoded, with byte or bit shuffle.
 // ---------------------------------------------------------------------------------------------
 bool lz4_decompress_block(const uint8_t* src, size_t n, uint8_t* dst, size_t cap) {
   size_t i = 0, o = 0;
@@ -312,9 +313,9 @@ std::vector<uint8_t> blosc_decompress(const uint8_t* f, size_t n, size_t expecte
   if (cbytes > n) throw bad("cbytes exceeds the stored size");
   if (expected != kAnySize && nbytes != expected) throw bad("decodes to an unexpected size");
   if (nbytes > max_bytes) throw VdbError(VdbError::InvalidBloscData, "Blosc frame: needs " + std::to_string(nbytes) + " bytes of room");
-  // a stream cannot expand by more than the codecs' run-length limits (LZ4 / BloscLZ: < 256x, zlib: ~1030x): a header that
-  // claims more than that from n stored bytes is corrupt
-  if (nbytes / 1100 > n) throw bad("claims more data than its streams can hold");
+  // a stream cannot expand by more than the codecs' run-length limits (LZ4 / BloscLZ: < 256x, zlib: ~1030x, Zstd: a 4-byte RLE
+  // block is 128 KiB): a header that claims more than that from n stored bytes is corrupt
+  if (nbytes / ((flags >> 5) == 4 ? 40000 : 1100) > n) throw bad("claims more data than its streams can hold");
   std::vector<uint8_t> out(nbytes);
   if (nbytes == 0) return out;
   if (flags & 0x2) {  // memcpyed
@@ -323,8 +324,8 @@ std::vector<uint8_t> blosc_decompress(const uint8_t* f, size_t n, size_t expecte
     return out;
   }
   const int codec = flags >> 5;
-  if (codec != 0 && codec != 1 && codec != 2 && codec != 3)
-    throw VdbError(VdbError::UnsupportedBloscFormat, "Blosc codec " + std::to_string(codec) + " is not supported (BloscLZ, LZ4, Snappy and zlib are; Zstd is not)");
+  if (codec > 4)
+    throw VdbError(VdbError::UnsupportedBloscFormat, "Blosc codec " + std::to_string(codec) + " is not supported (BloscLZ, LZ4, Snappy, zlib and Zstd are)");
   const bool byte_shuffled = (flags & 0x1) && typesize > 1, bit_shuffled = !byte_shuffled && (flags & 0x4) && blocksize >= typesize;
   if (blocksize == 0) throw bad("zero block size");
   const size_t nblocks = (nbytes + blocksize - 1) / blocksize;
@@ -352,6 +353,8 @@ std::vector<uint8_t> blosc_decompress(const uint8_t* f, size_t n, size_t expecte
         if (!blosclz_decompress_block(f + at, cb, d, neblock)) throw bad("corrupt BloscLZ stream");
       } else if (codec == 2) {
         if (!snappy_decompress_block(f + at, cb, d, neblock)) throw bad("corrupt Snappy stream");
+      } else if (codec == 4) {
+        if (!zstd_decompress_block(f + at, cb, d, neblock)) throw bad("corrupt Zstd stream");
       } else {
         uLongf dlen = (uLongf)neblock;
         if (uncompress(d, &dlen, f + at, (uLong)cb) != Z_OK || dlen != neblock) throw bad("corrupt zlib stream");

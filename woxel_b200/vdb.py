@@ -204,7 +204,7 @@ class VDB345:
 
 
 def blosc_decompress(frame: bytes) -> bytes:
-    """One c-blosc 1.x frame as the reader meets them inside a .vdb (read.rs:514-533): BloscLZ / LZ4 / zlib, byte or bit shuffle."""
+    """One c-blosc 1.x frame as the reader meets them inside a .vdb (read.rs:514-533): BloscLZ / LZ4 / Snappy / zlib / Zstd, byte or bit shuffle."""
     need = C.c_size_t(0)
     if len(frame) >= 16:
         need.value = int.from_bytes(frame[4:8], "little")
