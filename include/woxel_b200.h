@@ -180,7 +180,8 @@ int wx_tree_build(WxContext *ctx, const WxTreeDesc *topo, WxTree **out, WxSdfInf
 
 /*
  * One frame per state (n_states > 1 = camera batch).  Blocking.  rgba_out is HOST memory,
- * n_states x height x width x 4 bytes (pinned memory makes the read-back faster; pageable works) -- or device memory
+ * n_states x height x width x 4 bytes (pinned memory -- wx_host_alloc_pinned -- lets the copies overlap the rendering; pageable memory
+ * works: every kernel is then enqueued before the first copy, because a copy into pageable memory blocks the host until it is done) -- or device memory
  * of ANY GPU of the process's unified address space (another GPU's buffer, also one opened with wx_ipc_open): the frame
  * is then delivered there by DMA, chunk by chunk while later chunks render; that is how one process per GPU gathers its
  * frames on GPU 0 over NVLink (bench.py).  aov_out is host memory.

@@ -265,3 +265,47 @@ def test_long_tiles_first_changes_no_pixel(gpu_ctx):
         gpu_ctx.set_option(_ffi.WX_OPT_LONG_FIRST, 1)
         gpu_ctx.check(lib.wx_device_free(gpu_ctx._h, 0, buf))
         tree.free()
+
+
+@pytest.mark.parametrize("shape", [(1920, 1080, 1), (1283, 1083, 1), (640, 360, 19), (320, 200, 70)])
+def test_pinned_and_pageable_destinations_agree(shape):
+    """wx_render pipelines a large frame / a camera batch out of the device(s) chunk by chunk.  Into PINNED host memory the
+    copies are asynchronous and overlap the later chunks; into PAGEABLE memory (a numpy array, what most tests pass) a copy
+    blocks the host, so every kernel is enqueued first and the copies follow (host_pageable, wx_api.cu).  Both orders must
+    deliver the frames the device holds -- on one device and on a multi-device context, poisoned buffers first."""
+    w, h, n_cam = shape
+    s = scenes.get_scene("icosahedron")
+    cams = [scenes.CAMERAS["default"], scenes.CAMERAS["oblique_a"], scenes.CAMERAS["oblique_b"]]
+    states = [to_wx(scenes.state_for(*cams[k % 3], w, h, mode=(0, 3, 4, 1, 2)[k % 5])) for k in range(n_cam)]
+    lib = _ffi.cuda_lib()
+    nb = n_cam * w * h * 4
+    import torch
+    ids = list(range(min(4, torch.cuda.device_count()))) if torch.cuda.device_count() >= 2 else [0, 0]
+    one, many = W.Context(), W.Context(n_devices=len(ids), device_ids=ids)
+    pinned = C.c_void_p()
+    one.check(lib.wx_host_alloc_pinned(nb, C.byref(pinned)))
+    try:
+        out_pinned = np.frombuffer((C.c_uint8 * nb).from_address(pinned.value), np.uint8).reshape(n_cam, h, w, 4)
+        out_pageable = np.empty((n_cam, h, w, 4), np.uint8)
+        t1, tn = one.upload(s.desc()), many.upload(s.desc())
+        # the reference: frame by frame on the device, read back with a plain copy
+        buf = C.c_void_p()
+        one.check(lib.wx_device_alloc(one._h, 0, w * h * 4, C.byref(buf)))
+        ref = np.zeros((n_cam, h, w, 4), np.uint8)
+        for k in range(n_cam):
+            one.render_device(t1, states[k], w, h, buf.value)
+            one.check(lib.wx_stream_synchronize(one._h, 0, None))
+            one.check(lib.wx_memcpy_d2h(one._h, 0, ref[k].ctypes.data, buf, w * h * 4, None))
+            one.check(lib.wx_stream_synchronize(one._h, 0, None))
+        one.check(lib.wx_device_free(one._h, 0, buf))
+        for ctx, tree in ((one, t1), (many, tn)):
+            for rep in range(2):
+                for out in (out_pinned, out_pageable):
+                    out[:] = 0xA5
+                    got, _ = ctx.render(tree, states if n_cam > 1 else states[0], w, h, out=out)
+                    assert np.array_equal(got, ref), (ctx.device_count, rep, out is out_pinned)
+        del out_pinned
+        t1.free(), tn.free()
+    finally:
+        one.check(lib.wx_host_free_pinned(pinned))
+        one.close(), many.close()

@@ -841,6 +841,18 @@ extern "C" int wx_render_device(WxContext* ctx, int device_index, const WxTree* 
   return fail(nullptr, WX_ERR_UNSUPPORTED, "wx_render_device: unexpected exception");
 }
 
+// Pageable host memory: a device-to-host cudaMemcpyAsync into it returns only when the copy is done (the driver stages it), so a
+// call that alternates launches and copies would serialise them.  The pipelined paths then enqueue every kernel first and copy
+// afterwards; chunks still leave in order while later ones render, but overlap of the copies themselves needs wx_host_alloc_pinned.
+static bool host_pageable(const void* p) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return true;
+  }
+  return at.type == cudaMemoryTypeUnregistered;
+}
+
 static int ensure(WxContext* ctx, void** p, size_t* have, size_t need) {
   if (*have >= need) return WX_OK;
   if (*p) (void)cudaFree(*p);
@@ -897,6 +909,9 @@ static int render_distributed(WxContext* ctx, const WxTree* tree, const WxState*
     for (uint32_t r = 0; r < height; r += rows) chunks.push_back(Chunk{0, 1, r, std::min(height, r + rows)});
   }
   const uint32_t n_chunks = (uint32_t)chunks.size();
+  // Pageable destination: pass 0 enqueues every device's kernels, pass 1 copies (host_pageable); else one pass does both.
+  const bool deferred = host_pageable(rgba_out);
+  for (int pass = 0; pass < (deferred ? 2 : 1); ++pass)
   for (int i = 0; i < ndev; ++i) {
     DeviceSlot& s = ctx->dev[i];
     WX_CUDA(ctx, cudaSetDevice(s.id));
@@ -905,6 +920,21 @@ static int render_distributed(WxContext* ctx, const WxTree* tree, const WxState*
       int rc = ensure(ctx, (void**)&s.scratch, &s.scratch_bytes, npix * 4);
       if (rc) return rc;
       local = s.scratch;
+    }
+    if (pass == 1) {  // the copies of a pageable destination, each behind its chunk's kernel
+      if (n_chunks == 1) {
+        WX_CUDA(ctx, copy_own_bands(rgba_out, local, i, ndev, 0, n_states, 0, height, width, height, cudaMemcpyDefault, s.stream));
+      } else {
+        for (uint32_t c_idx = 0; c_idx < n_chunks; ++c_idx) {
+          const Chunk& ch = chunks[c_idx];
+          WX_CUDA(ctx, cudaStreamWaitEvent(s.copy_stream, s.chunk_done[c_idx], 0));
+          WX_CUDA(ctx, copy_own_bands(rgba_out, local, i, ndev, ch.cam0, ch.cam1, ch.row0, ch.row1, width, height, cudaMemcpyDefault, s.copy_stream));
+        }
+        WX_CUDA(ctx, cudaEventRecord(s.fork, s.copy_stream));
+        WX_CUDA(ctx, cudaStreamWaitEvent(s.stream, s.fork, 0));
+      }
+      WX_CUDA(ctx, cudaEventRecord(s.join[0], s.stream));  // kernels and copies of this device
+      continue;
     }
     while (s.chunk_done.size() < n_chunks) {
       cudaEvent_t e;
@@ -930,7 +960,7 @@ static int render_distributed(WxContext* ctx, const WxTree* tree, const WxState*
       if (rc) return rc;
       *launches += l;
       WX_CUDA(ctx, cudaEventRecord(s.ev1, s.stream));
-      WX_CUDA(ctx, copy_own_bands(rgba_out, local, i, ndev, 0, n_states, 0, height, width, height, cudaMemcpyDefault, s.stream));
+      if (!deferred) WX_CUDA(ctx, copy_own_bands(rgba_out, local, i, ndev, 0, n_states, 0, height, width, height, cudaMemcpyDefault, s.stream));
     } else {
       WX_CUDA(ctx, cudaEventRecord(s.fork, s.stream));
       cudaStream_t ks[3] = {s.stream, s.aux[0], s.aux[1]};
@@ -944,18 +974,20 @@ static int render_distributed(WxContext* ctx, const WxTree* tree, const WxState*
         if (rc) return rc;
         *launches += l;
         WX_CUDA(ctx, cudaEventRecord(s.chunk_done[c_idx], st));
-        WX_CUDA(ctx, cudaStreamWaitEvent(s.copy_stream, s.chunk_done[c_idx], 0));
-        WX_CUDA(ctx, copy_own_bands(rgba_out, local, i, ndev, ch.cam0, ch.cam1, ch.row0, ch.row1, width, height, cudaMemcpyDefault, s.copy_stream));
+        if (!deferred) WX_CUDA(ctx, cudaStreamWaitEvent(s.copy_stream, s.chunk_done[c_idx], 0));
+        if (!deferred) WX_CUDA(ctx, copy_own_bands(rgba_out, local, i, ndev, ch.cam0, ch.cam1, ch.row0, ch.row1, width, height, cudaMemcpyDefault, s.copy_stream));
       }
       for (int k = 0; k < 2; ++k) {
         WX_CUDA(ctx, cudaEventRecord(s.join[k], s.aux[k]));
         WX_CUDA(ctx, cudaStreamWaitEvent(s.stream, s.join[k], 0));
       }
       WX_CUDA(ctx, cudaEventRecord(s.ev1, s.stream));  // all kernels of this device
-      WX_CUDA(ctx, cudaEventRecord(s.fork, s.copy_stream));
-      WX_CUDA(ctx, cudaStreamWaitEvent(s.stream, s.fork, 0));
+      if (!deferred) {
+        WX_CUDA(ctx, cudaEventRecord(s.fork, s.copy_stream));
+        WX_CUDA(ctx, cudaStreamWaitEvent(s.stream, s.fork, 0));
+      }
     }
-    WX_CUDA(ctx, cudaEventRecord(s.join[0], s.stream));  // kernels and copies of this device
+    if (!deferred) WX_CUDA(ctx, cudaEventRecord(s.join[0], s.stream));  // kernels and copies of this device
   }
   WX_CUDA(ctx, cudaSetDevice(d0.id));
   for (int i = 1; i < ndev; ++i) WX_CUDA(ctx, cudaStreamWaitEvent(d0.stream, ctx->dev[i].join[0], 0));
@@ -1085,6 +1117,7 @@ extern "C" int wx_render(WxContext* ctx, const WxTree* tree, const WxState* stat
       WX_CUDA(ctx, cudaEventRecord(d0.fork, d0.stream));
       cudaStream_t ks[3] = {d0.stream, d0.aux[0], d0.aux[1]};
       for (int k = 0; k < 2; ++k) WX_CUDA(ctx, cudaStreamWaitEvent(d0.aux[k], d0.fork, 0));
+      const bool deferred = host_pageable(rgba_out);
       for (size_t c = 0; c < chunks.size(); ++c) {
         const Chunk& ch = chunks[c];
         cudaStream_t st = ks[c % 3];
@@ -1095,10 +1128,18 @@ extern "C" int wx_render(WxContext* ctx, const WxTree* tree, const WxState* stat
         if (rc) return rc;
         launches += l;
         WX_CUDA(ctx, cudaEventRecord(d0.chunk_done[c], st));
+        if (deferred) continue;  // pageable destination: every launch first (host_pageable)
         WX_CUDA(ctx, cudaStreamWaitEvent(d0.copy_stream, d0.chunk_done[c], 0));
         const size_t off = ((size_t)ch.cam0 * height + ch.row0) * width * 4;
         const size_t bytes = ch.ncam > 1 || ch.row1 - ch.row0 == height ? (size_t)ch.ncam * height * width * 4 : (size_t)(ch.row1 - ch.row0) * width * 4;
         WX_CUDA(ctx, cudaMemcpyAsync(rgba_out + off, ctx->fb.rgba + off, bytes, cudaMemcpyDefault, d0.copy_stream));  // host, or any GPU's memory (UVA)
+      }
+      for (size_t c = 0; deferred && c < chunks.size(); ++c) {
+        const Chunk& ch = chunks[c];
+        WX_CUDA(ctx, cudaStreamWaitEvent(d0.copy_stream, d0.chunk_done[c], 0));
+        const size_t off = ((size_t)ch.cam0 * height + ch.row0) * width * 4;
+        const size_t bytes = ch.ncam > 1 || ch.row1 - ch.row0 == height ? (size_t)ch.ncam * height * width * 4 : (size_t)(ch.row1 - ch.row0) * width * 4;
+        WX_CUDA(ctx, cudaMemcpyAsync(rgba_out + off, ctx->fb.rgba + off, bytes, cudaMemcpyDefault, d0.copy_stream));
       }
       // join: the main stream waits for the other kernel streams (ev1 = all kernels done), then for the last copy
       for (int k = 0; k < 2; ++k) {
