@@ -31,7 +31,6 @@ using namespace wx;
 // ---------------------------------------------------------------------------------------------
 // Context
 // ---------------------------------------------------------------------------------------------
-constexpr uint32_t kCounterRing = 256;  // launches that may be in flight on one device before a counter is reused
 
 // Long-tiles-first state (wx_internal.h TileSched) of ONE launch geometry on ONE stream: two sets of (list, flags), the
 // previous launch's and the one being recorded, swapped after every launch; a high-priority stream for the long-tile kernel.
@@ -135,8 +134,6 @@ struct DeviceSlot {
   uint32_t states_cap = 0;
   uint8_t* scratch = nullptr;  // staging frame when peer stores are impossible
   size_t scratch_bytes = 0;
-  uint32_t* counters = nullptr;  // work-queue heads of the persistent kernel, one per launch in flight (ring of kCounterRing)
-  uint32_t counter_next = 0;
   uint32_t resident_ctas = 0;    // SM count x CTAs per SM
   cudaStream_t copy_stream = nullptr;   // read-back of finished row chunks while later chunks render
   cudaStream_t aux[2] = {nullptr, nullptr};  // chunks alternate over stream/aux[0]/aux[1] so that one chunk's drain overlaps the next
@@ -352,7 +349,6 @@ extern "C" int wx_init(int n_devices, const int* device_ids, WxContext** out) tr
     cudaError_t err = cudaSetDevice(s.id);
     if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking);
     if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&s.copy_stream, cudaStreamNonBlocking);
-    if (err == cudaSuccess) err = cudaMalloc(&s.counters, kCounterRing * sizeof(uint32_t));
     if (err == cudaSuccess) {
       int sms = 0;
       err = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s.id);
@@ -417,7 +413,6 @@ extern "C" int wx_shutdown(WxContext* ctx) {
     s.sched.clear();
     if (s.d_states) (void)cudaFree(s.d_states);
     if (s.scratch) (void)cudaFree(s.scratch);
-    if (s.counters) (void)cudaFree(s.counters);
     if (s.ev0) (void)cudaEventDestroy(s.ev0);
     if (s.ev1) (void)cudaEventDestroy(s.ev1);
     for (cudaEvent_t e : s.chunk_done) (void)cudaEventDestroy(e);
@@ -750,7 +745,16 @@ static int launch_on(WxContext* ctx, int dev_i, const WxTree* tree, const WxStat
     else P.shard_index = 0, P.shard_count = 1, P.band_rows = 0;
     P.row_base = row0, P.row_end = row1;
     uint32_t l = 0;
-    uint32_t* counter = s.counters + (s.counter_next++ % kCounterRing);
+    // work-queue head of a persistent kernel (WX_OPT_KERNEL != 0): allocated and freed in stream order, so that launches on
+    // different streams never share one however many are in flight (a ring of counters could be reused too early)
+    uint32_t* counter = nullptr;
+    if (ctx->opt.kernel != 0) {
+      const cudaError_t ae = cudaMallocAsync((void**)&counter, sizeof(uint32_t), stream);
+      if (ae != cudaSuccess) {
+        if (launch_states) (void)cudaFreeAsync(launch_states, stream);
+        return fail_cuda(ctx, ae, "render: work counter");
+      }
+    }
     // long-tiles-first state of this launch geometry on this stream (plain launches when the option is off)
     SchedEntry* se = frame_sched;
     P.prev_list = nullptr, P.prev_flag = nullptr, P.next_list = nullptr, P.next_flag = nullptr;
@@ -762,6 +766,7 @@ static int launch_on(WxContext* ctx, int dev_i, const WxTree* tree, const WxStat
       se = find_sched(s, key);
     }
     const cudaError_t le = launch_raycast(P, e - b, mode, stream, &l, counter, s.resident_ctas, ctx->opt, se, sched_call);
+    if (counter) (void)cudaFreeAsync(counter, stream);  // behind the kernel that used it
     if (le == cudaSuccess && se && P.next_list && !sched_call) se->launched();  // (a chunked frame: the caller, after its last chunk)
     if (le != cudaSuccess) {
       if (launch_states) (void)cudaFreeAsync(launch_states, stream);
